@@ -1,0 +1,53 @@
+// airgpu_kernels.cuh -- device-side interface of the ADS-B decode stage (sm_100a).
+//
+// One fused kernel per capture does the whole reference path
+//   IQ -> magnitude -> preamble/DF gate -> bit slice -> CRC-24 (+1-bit repair) -> frame list
+// (reference src/adsb.rs:92-122 and what it calls); two small kernels then put
+// the per-tile frame lists into the reference's emission order.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/airgpu.h"
+
+namespace airgpu {
+
+// ---- tiling ---------------------------------------------------------------
+constexpr int kTile = 8192;             // candidate offsets per CTA
+constexpr int kHalo = 256;              // a candidate at i reads samples [i, i+240): 239 needed, 256 keeps 16-byte chunks
+constexpr int kLevels = kTile + kHalo;  // u16 levels staged in shared memory per tile
+constexpr int kChunks = kLevels / 8;    // 16-byte chunks (8 levels each)
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kBitmapWords = kTile / 32;
+constexpr int kStagePerWarp = 16;       // frames a warp can stage before falling back to recompute
+constexpr int kFrameSamples = 240;      // 16 + 112 * 2, reference src/adsb.rs:98
+
+struct DecodeParams {
+    const void *iq;                 // interleaved IQ, device memory
+    unsigned long long n_samples;   // complex samples in the capture
+    unsigned long long seg_len;     // samples per independent segment (>= 1)
+    unsigned int tiles_per_seg;
+    unsigned int n_tiles;           // n_segments * tiles_per_seg
+    unsigned long long base_offset; // added to every frame offset
+    airgpu_frame *scratch;          // unordered-between-tiles frame records
+    unsigned long long cap;         // capacity of scratch (and of the final output)
+    unsigned long long *counters;   // [0] frames, [1] gate passes, [2] preamble passes
+    uint2 *tile_tab;                // per tile: (base index into scratch, frame count)
+};
+
+enum { kCounterFrames = 0, kCounterGate = 1, kCounterPreamble = 2, kNumCounters = 4 };
+
+// Launchers (stream-ordered, no synchronisation inside).
+cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream);
+// Ordered frames are appended to `out` at index *d_total (device counter, updated in place).
+cudaError_t launch_finalize(const DecodeParams &p, unsigned long long *tile_pos, airgpu_frame *out,
+                            unsigned long long *d_total, cudaStream_t stream);
+
+// Exhaustive self-check helper used by the tests: level (inverted magnitude proxy)
+// the kernel computes for every U8 (I, Q) pair / for a list of CS16 samples.
+cudaError_t launch_levels_u8(uint16_t *out65536, cudaStream_t stream);
+cudaError_t launch_levels_cs16(const int16_t *iq, unsigned long long n, uint16_t *out, cudaStream_t stream);
+
+}  // namespace airgpu

@@ -1,0 +1,161 @@
+/*
+ * airgpu.h -- C ABI of the B200 ADS-B / Mode S decode stage.
+ *
+ * This library is a drop-in for ONE thread of jaxsonpd/air_rs: the body of
+ *     fn process_sdr_data_thread(rx: Receiver<Vec<Complex<i16>>>, tx: Sender<AdsbPacket>)
+ * (reference src/adsb.rs:92-122, spawned at src/adsb.rs:147), i.e.
+ *     get_magnitude            src/utils.rs:46-52
+ *     check_for_adsb_packet    src/adsb/demod.rs:17-57
+ *     extract_packet           src/adsb/demod.rs:65-82  (slicer :92-131, :180-201)
+ *     get_adsb_crc             src/adsb/crc.rs:10-40
+ *     try_crc_recovery         src/adsb/crc.rs:49-65
+ * Everything before it (SDR / playback threads) and after it
+ * (AdsbPacket::new, aircraft tracking, TUI / web) stays in the Rust host.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions, no unwinding across the boundary;
+ *   - every call returns AIRGPU_OK (0) or a negative airgpu_status;
+ *     airgpu_last_error() gives the message for the calling thread;
+ *   - there is NO CPU fallback: without a CUDA device airgpu_create fails;
+ *   - a context is used by one thread at a time (the reference has exactly one
+ *     decode thread, src/adsb.rs:147).
+ *
+ * Semantics (bit-exact with the reference's CPU decode)
+ *   A capture of n_samples complex samples is cut into independent segments of
+ *   segment_samples (0 = the whole capture is one segment).  Within a segment
+ *   of length L every offset i in [0, L-240) is tested in ascending order
+ *   (src/adsb.rs:98); a frame is emitted for every i that passes the gate and
+ *   whose CRC matches or is repairable -- there is NO skip after a hit and NO
+ *   de-duplication (src/adsb.rs:113 is a no-op).  L < 240, which panics in the
+ *   reference, yields zero frames here (the one deliberate deviation).
+ *   segment_samples = 20000 reproduces the reference's playback chunking
+ *   (src/adsb.rs:78); one segment per received buffer reproduces the SDR path.
+ */
+#ifndef AIRGPU_H
+#define AIRGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIRGPU_ABI_VERSION 1
+
+typedef enum airgpu_status {
+    AIRGPU_OK = 0,
+    AIRGPU_ERR_INVALID = -1,    /* bad argument                                   */
+    AIRGPU_ERR_NO_DEVICE = -2,  /* no CUDA device / wrong architecture            */
+    AIRGPU_ERR_CUDA = -3,       /* a CUDA call failed; see airgpu_last_error()    */
+    AIRGPU_ERR_NOMEM = -4,      /* host or device allocation failed               */
+    AIRGPU_ERR_OVERFLOW = -5,   /* more frames than the output capacity           */
+    AIRGPU_ERR_BUSY = -6,       /* ring full: collect before submitting more      */
+    AIRGPU_ERR_TICKET = -7      /* unknown or already collected ticket            */
+} airgpu_status;
+
+/* Sample formats.  CS16 is what the reference receives (Vec<Complex<i16>>,
+ * src/adsb.rs:54-59: interleaved little-endian i16 I,Q -- 4 bytes/sample).
+ * U8 is the RTL-SDR native format BASELINE.json names (interleaved unsigned
+ * I,Q bytes -- 2 bytes/sample); it is DEFINED as CS16 with
+ * re = (2*u - 255) * 128 and decoded with identical results. */
+typedef enum airgpu_format {
+    AIRGPU_FMT_CS16 = 0,
+    AIRGPU_FMT_U8 = 1
+} airgpu_format;
+
+/* One decoded frame.  `bytes` is exactly the Vec<u8> the reference passes to
+ * AdsbPacket::new (src/adsb.rs:107, src/adsb/packet.rs:25).  `offset` and
+ * `fixed_bit` do not exist in the reference's output; they are derived from its
+ * control flow (loop index at src/adsb.rs:98; flipped bit at src/adsb/crc.rs:52-55). */
+typedef struct airgpu_frame {
+    uint8_t  bytes[14];
+    uint8_t  fixed_bit;   /* 0xFF = CRC matched as received; else repaired data bit 0..87 (MSB first) */
+    uint8_t  reserved;    /* 0 */
+    uint64_t offset;      /* base_offset + segment start + i (preamble start, in samples) */
+} airgpu_frame;           /* 24 bytes */
+
+typedef struct airgpu_config {
+    uint32_t struct_size;        /* sizeof(airgpu_config), for ABI evolution            */
+    int32_t  device;             /* CUDA device ordinal                                  */
+    uint32_t format;             /* airgpu_format                                        */
+    uint32_t ring_slots;         /* streaming ring depth (0 -> 4)                        */
+    uint64_t max_buffer_samples; /* largest buffer airgpu_submit will see (0 -> 262144)  */
+    uint64_t max_frames;         /* output capacity per submit / per decode call (0 -> auto) */
+} airgpu_config;
+
+typedef struct airgpu_ctx airgpu_ctx;
+
+/* Counters of the last completed decode call on this context. */
+typedef struct airgpu_stats {
+    uint64_t n_samples;
+    uint64_t n_frames;       /* frames produced (may exceed the capacity on overflow)   */
+    uint64_t gate_passes;    /* the reference's num_processed counter, src/adsb.rs:105  */
+    uint64_t n_tiles;
+    float    kernel_ms;      /* device time of the decode kernels (CUDA events), 0 if not measured */
+    float    h2d_ms;         /* host->device copy time of the last host-buffer decode   */
+} airgpu_stats;
+
+const char *airgpu_version(void);
+const char *airgpu_last_error(void);
+int airgpu_device_count(void);
+
+/* Replaces the setup the reference does with expect() at src/adsb.rs:35-48 /
+ * :126-147: returns an error code instead of panicking. */
+int airgpu_create(const airgpu_config *cfg, airgpu_ctx **out);
+void airgpu_destroy(airgpu_ctx *ctx);
+
+/* ---- streaming: the loop body of process_sdr_data_thread ----------------- *
+ * submit  == `while let Ok(buf) = rx.recv()` (src/adsb.rs:95): copies the buffer
+ *            into a pinned ring slot, queues H2D on the copy stream and the
+ *            decode on the compute stream, and returns at once.
+ * collect == the frames that buffer yields, ascending offset, in the order the
+ *            reference would tx.send() them (src/adsb.rs:107-111).  Tickets
+ *            must be collected in submission order.  Each buffer is one
+ *            independent segment (no state across buffers, as in the reference). */
+int airgpu_submit(airgpu_ctx *ctx, const void *iq, size_t n_samples,
+                  uint64_t base_offset, uint64_t *ticket);
+int airgpu_collect(airgpu_ctx *ctx, uint64_t ticket, airgpu_frame *out, size_t cap,
+                   size_t *n_frames);
+
+/* ---- one-shot decode of a capture held in HOST memory -------------------- *
+ * Chunks the capture through the pinned ring (H2D overlapped with compute,
+ * 240-sample overlap between chunks inside a segment) and returns the frames
+ * in reference order.  segment_samples as described above; n_streams batches
+ * of equal length are just segment_samples = samples per stream. */
+int airgpu_decode(airgpu_ctx *ctx, const void *iq, size_t n_samples,
+                  size_t segment_samples, uint64_t base_offset,
+                  airgpu_frame *out, size_t cap, size_t *n_frames);
+
+/* ---- decode of a capture already resident in DEVICE memory --------------- *
+ * d_iq and d_out are device pointers on the context's device; d_out holds
+ * `cap` records.  `stream` is a cudaStream_t (NULL = the context's compute
+ * stream).  Asynchronous: the frame count lands in *d_count (device, 8 bytes)
+ * and is also returned by airgpu_sync_count() after the stream is drained.
+ * Shards of a long capture call this once per GPU with base_offset = first
+ * sample of the shard and n_samples including the 240-sample right halo. */
+int airgpu_decode_device(airgpu_ctx *ctx, const void *d_iq, size_t n_samples,
+                         size_t segment_samples, uint64_t base_offset,
+                         airgpu_frame *d_out, size_t cap, uint64_t *d_count,
+                         void *stream);
+int airgpu_sync_count(airgpu_ctx *ctx, uint64_t *n_frames);
+
+int airgpu_get_stats(airgpu_ctx *ctx, airgpu_stats *out);
+
+/* Page-locked host buffers ("pinned host ring buffers"): a receive thread that
+ * fills buffers from airgpu_host_alloc lets airgpu_decode copy asynchronously
+ * straight from them.  Replaces the plain Vec allocations at src/adsb.rs:60,64,78. */
+int airgpu_host_alloc(size_t bytes, void **out);
+int airgpu_host_free(void *p);
+
+/* ---- diagnostics (device arithmetic only; used by the parity tests) ------- *
+ * The per-sample "level" the kernel compares instead of the magnitude:
+ *   U8  : out[I | Q << 8] for all 65536 byte pairs;
+ *   CS16: out[k] = 65535 - floor(sqrt(re_k^2 + im_k^2)). */
+int airgpu_dbg_levels_u8(airgpu_ctx *ctx, uint16_t *out65536);
+int airgpu_dbg_levels_cs16(airgpu_ctx *ctx, const int16_t *iq, size_t n_samples, uint16_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIRGPU_H */

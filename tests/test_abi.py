@@ -1,0 +1,65 @@
+"""CPU tests of the boundary: the shared library builds for sm_100a, loads, exports
+every symbol the headers declare, and refuses to run without a GPU (no fallback)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from air_rs_b200 import build, native
+from air_rs_b200.decoder import AdsbDecoder
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def declared_symbols(header: Path):
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(airgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    path = build.build()
+    assert path.exists() and path.parent == ROOT / "air_rs_b200" / "_lib"
+    lib = native.lib()
+    assert b"sm_100a" in lib.airgpu_version()
+
+
+@pytest.mark.parametrize("header", ["airgpu.h", "airgpu_synth.h"])
+def test_every_declared_symbol_is_exported(header):
+    names = declared_symbols(ROOT / "include" / header)
+    assert len(names) >= 4
+    raw = C.CDLL(str(build.build()))
+    missing = [n for n in names if not hasattr(raw, n)]
+    assert not missing, f"declared in {header} but not exported: {missing}"
+    bound = set(native.SYMBOLS) | set(native.SYNTH_SYMBOLS)
+    assert set(names) <= bound, f"not bound in native.py: {sorted(set(names) - bound)}"
+
+
+def test_frame_record_layout():
+    assert native.FRAME_DTYPE.itemsize == 24
+    assert native.FRAME_DTYPE.fields["fixed_bit"][1] == 14
+    assert native.FRAME_DTYPE.fields["offset"][1] == 16
+    assert C.sizeof(native.Config) == 32
+
+
+def test_sass_is_sm100_and_uses_packed_minmax():
+    out = subprocess.run(["cuobjdump", "-sass", str(build.build())], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "VIMNMX3.U16x2" in out and "IDP.4A" in out
+    assert "airgpu" in out
+
+
+def test_no_cpu_fallback(has_gpu):
+    if has_gpu:
+        pytest.skip("a GPU is present; the fallback check is for GPU-less machines")
+    with pytest.raises(native.AirgpuError) as ei:
+        AdsbDecoder()
+    assert ei.value.code == native.ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "air_rs_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        text = f.read_text()
+        assert "oracle" not in text.replace("no oracle", "") or f.name in ("__init__.py",), f
