@@ -81,8 +81,8 @@ struct airgpu_ctx {
     size_t max_buffer_samples = 0;
     size_t max_frames = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr, ev_sync = nullptr;
-    bool ev_valid = false, evh_valid = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr, ev_sync = nullptr, evk0 = nullptr, evk1 = nullptr;
+    bool ev_valid = false, evh_valid = false, evk_valid = false;
 
     // workspace shared by every decode on the compute stream (stream-ordered reuse)
     airgpu_frame *scratch = nullptr;
@@ -175,7 +175,10 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.cap = cap;
     p.counters = c->counters;
     p.tile_tab = c->tile_tab;
+    CU(cudaEventRecord(c->evk0, stream));
     CU(launch_decode(c->format, p, stream));
+    CU(cudaEventRecord(c->evk1, stream));
+    c->evk_valid = true;
     CU(launch_finalize(p, c->tile_pos, d_out, d_total, stream));
     c->stats.n_tiles += g.n_tiles;
     c->stats.n_samples += n;
@@ -232,7 +235,7 @@ void airgpu_destroy(airgpu_ctx *c)
     if (c->counters) cudaFree(c->counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->out_dev) cudaFree(c->out_dev);
-    for (cudaEvent_t e : {c->ev0, c->ev1, c->evh0, c->evh1, c->ev_sync})
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->evh0, c->evh1, c->ev_sync, c->evk0, c->evk1})
         if (e) cudaEventDestroy(e);
     if (c->compute) cudaStreamDestroy(c->compute);
     if (c->copy) cudaStreamDestroy(c->copy);
@@ -286,6 +289,8 @@ int airgpu_create(const airgpu_config *cfg, airgpu_ctx **out)
     CUX(cudaEventCreate(&c->ev1));
     CUX(cudaEventCreate(&c->evh0));
     CUX(cudaEventCreate(&c->evh1));
+    CUX(cudaEventCreate(&c->evk0));
+    CUX(cudaEventCreate(&c->evk1));
     CUX(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     CUX(cudaMalloc(&c->counters, (kNumCounters + 1) * sizeof(unsigned long long)));
     CUX(cudaMemset(c->counters, 0, (kNumCounters + 1) * sizeof(unsigned long long)));
@@ -371,6 +376,12 @@ int airgpu_get_stats(airgpu_ctx *c, airgpu_stats *out)
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         c->stats.kernel_ms = ms;
+    }
+    if (c->evk_valid) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(c->evk1));
+        CU(cudaEventElapsedTime(&ms, c->evk0, c->evk1));
+        c->stats.decode_ms = ms;
     }
     if (c->evh_valid) {
         float ms = 0.f;

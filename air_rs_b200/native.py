@@ -50,6 +50,8 @@ class Stats(C.Structure):
         ("n_tiles", C.c_uint64),
         ("kernel_ms", C.c_float),
         ("h2d_ms", C.c_float),
+        ("decode_ms", C.c_float),
+        ("reserved", C.c_float),
     ]
 
 

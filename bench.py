@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- Msamples/s, IQ -> ordered CRC-valid frames, on N B200s of one node.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line from rank 0.  For N > 1 it is launched under torchrun, one
+rank per GPU.
+
+Workload (config.workload): BASELINE.json configs[4], the 1 h synthetic capture --
+8 640 000 000 complex samples of interleaved u8 IQ (17.28 GB), dense traffic
+(config 2's mix: ~3000 DF17/s + ~3000 DF4/5/11/20/21 decoys/s, SNR 8..30 dB,
+overlaps allowed) on a 10 s schedule that repeats while the noise never does.
+It is rendered ON THE DEVICE by the integer-only generator (air_rs_b200/synth.py,
+csrc/airgpu_synth.cu).  Frames are modulated at the reference's
+fixed 2 samples/us; "2.4 MS/s" fixes sample counts only.  The metric is quoted
+on this configuration ("target: >= 60 % of HBM roofline per GPU on a 1 h
+synthetic capture"), and it fits one GPU, so it is the N = 1 workload too.
+
+A step = one pass of the whole hot path over the capture: decode kernel +
+ordering (scan, gather) into the reference-ordered frame list; for N > 1 the
+capture is cut into N contiguous candidate ranges (+240-sample halo), one per
+rank, and the per-rank lists are all-gathered over NCCL ("scaling": "strong").
+Inputs (17 GB) are far larger than L2 (126 MB), so no explicit flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+TOTAL_SAMPLES = int(os.environ.get("AIRGPU_BENCH_SAMPLES", 8_640_000_000))
+PERIOD = 24_000_000            # the traffic schedule repeats every 10 s of capture
+SEED = 1090
+SIGMA = 2.0
+HALO = 240
+CPU_SAMPLE = int(os.environ.get("AIRGPU_CPU_SAMPLES", 240_000_000))   # bounded CPU sample: first 100 s of the capture
+REF_SAMPLE = int(os.environ.get("AIRGPU_REF_SAMPLES", 240_000_000))
+METRIC = "Msamples/s IQ->CRC-valid frames"
+UNIT = "Msamples/s"
+
+
+def traffic_table():
+    from air_rs_b200 import synth
+
+    return synth.make_traffic(SEED, PERIOD, df17_per_s=3000.0, decoy_per_s=3000.0, snr_db=(8.0, 30.0), sigma=SIGMA)
+
+
+def workload_config(n_gpus: int, total: int) -> dict:
+    return {
+        "workload": f"config5: 1 h synthetic capture, {total} samples u8 IQ ({2 * total / 1e9:.2f} GB), dense traffic "
+                    "(3000 DF17/s + 3000 decoys/s, SNR 8-30 dB, 10 s schedule repeated, noise never repeats), "
+                    "frames modulated at the reference's fixed 2 samples/us",
+        "format": "u8",
+        "mode": "continuous",
+        "sharding": f"{n_gpus} contiguous candidate ranges + 240-sample halo" if n_gpus > 1 else "none",
+        "l2": "inputs (>= 2 GB per GPU) larger than the 126 MB L2; no flush needed",
+        "generator_seed": SEED,
+    }
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock / throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.active = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self._stop_evt.is_set():
+                if self.active.is_set():
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.002)
+        except Exception as e:  # NVML missing: report what we know
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+
+    def summary(self) -> dict:
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def shard_bounds(total: int, n: int):
+    cands = total - HALO
+    b = [(cands * k // n) // 8192 * 8192 for k in range(n)] + [cands]
+    return b
+
+
+def run_ours(args):
+    import torch
+
+    from air_rs_b200 import synth
+    from air_rs_b200.decoder import AdsbDecoder
+    from air_rs_b200.native import FMT_U8, FRAME_DTYPE
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: F811
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    total = TOTAL_SAMPLES
+    bounds = shard_bounds(total, world)
+    a, b = bounds[rank], bounds[rank + 1]
+    n_local = b - a + HALO                      # candidates [a, b) need samples [a, b + 240)
+
+    table = traffic_table()
+    gen = synth.DeviceSynth(table, device=local)
+    iq = gen.render(SEED, a, n_local, FMT_U8, SIGMA, period=PERIOD)
+    torch.cuda.synchronize()
+
+    dec = AdsbDecoder(fmt=FMT_U8, device=local)
+    cap = max(1 << 16, int(n_local / 240))      # ~3x the dense-traffic frame density
+    out = torch.empty((cap, FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+    counts_all = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    state = {"frames": 0, "gathered": None}
+
+    def decode_resident():
+        dec.decode_device(iq.data_ptr(), n_local, out.data_ptr(), cap, 0, a, d_count.data_ptr(), stream)
+
+    def gather():
+        """NCCL all-gather of the per-rank ordered lists (rank order == offset order)."""
+        dist.all_gather_into_tensor(counts_all, d_count)
+        counts = counts_all.cpu()
+        m = int(counts.max())
+        slab = torch.empty((world, m, FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(slab.view(-1), out[:m].reshape(-1))
+        state["gathered"] = (slab, counts)
+        state["frames"] = int(counts.sum())
+
+    def step():
+        decode_resident()
+        if world > 1:
+            gather()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.active.set()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.active.clear()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total = timed(step, args.steps, args.warmup, sampler)
+    sampler.stop()
+    ms_step = ms_total / args.steps
+    n_frames_local = int(d_count.item())
+    if world == 1:
+        state["frames"] = n_frames_local
+    if n_frames_local > cap:
+        raise SystemExit(f"frame capacity {cap} too small for {n_frames_local} frames")
+    value = total / (ms_step * 1e-3) / 1e6
+
+    # dominant kernel alone (CUDA events around the decode kernel on its launch stream)
+    k_ms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        decode_resident()
+        k_ms.append(dec.stats()["decode_ms"])
+    kernel_ms = float(np.mean(k_ms))
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 2.0 * n_local + 24.0 * n_frames_local
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.loads((ROOT / "profiles" / "latest_traffic.json").read_text()).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "traffic": traffic,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        "kernel": "decode_kernel<U8>", "kernel_ms": round(kernel_ms, 4),
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "nominal_hbm_gbs": 8000,
+    }
+
+    # ---- end to end: host (pinned) buffers through airgpu_decode, H2D + D2H inside the timed region
+    e2e = None
+    try:
+        h_iq = torch.empty(2 * n_local, dtype=torch.uint8, pin_memory=True)
+        h_iq.copy_(iq)
+        torch.cuda.synchronize()
+        h_out = np.zeros(cap, dtype=FRAME_DTYPE)
+        got = {"n": 0}
+
+        def e2e_step():
+            import ctypes as C
+
+            from air_rs_b200 import native
+
+            n_out = C.c_size_t(0)
+            native.check(native.lib().airgpu_decode(dec._h, h_iq.data_ptr(), n_local, 0, a, h_out.ctypes.data, cap,
+                                                    C.byref(n_out)))
+            got["n"] = n_out.value
+            if world > 1:
+                d_count.fill_(n_out.value)
+                out[: n_out.value].copy_(torch.from_numpy(h_out[: n_out.value].view(np.uint8).reshape(-1, 24)))
+                gather()
+
+        k2 = max(1, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        e2e_ms = timed(e2e_step, k2, 1)
+        wall = time.perf_counter() - t0
+        # airgpu_decode is synchronous (it returns the frames), so CUDA events bracket host-side work too
+        e2e_ms_step = e2e_ms / k2
+        e2e = {
+            "value": round(total / (e2e_ms_step * 1e-3) / 1e6, 1), "unit": UNIT,
+            "h2d_bytes_per_step": int(2 * n_local), "d2h_bytes_per_step": int(24 * got["n"] + 8),
+            "ms_per_step": round(e2e_ms_step, 3), "steps": k2,
+            "api": "airgpu_decode (C ABI), pinned host IQ -> host frame records",
+        }
+        del h_iq
+    except Exception as e:  # e.g. not enough pinned host memory for the shard
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "error": f"{type(e).__name__}: {e}"}
+
+    # ---- CPU baseline: the literal oracle on one core, bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle_c
+
+        ns = min(CPU_SAMPLE, n_local)
+        host = iq[: 2 * ns].cpu().numpy()
+        t0 = time.perf_counter()
+        lit, gate = oracle_c.decode_literal(host)
+        dt = time.perf_counter() - t0
+        ncores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        fast, _ = oracle_c.decode_fast(host, threads=ncores)
+        dt_fast = time.perf_counter() - t0
+        # same frames as the GPU on that slice?
+        out_host = AdsbDecoder.frames_from_tensor(out, n_frames_local)
+        sub = out_host[out_host["offset"] < ns - HALO]
+        cpu = {
+            "value": round(ns / dt / 1e6, 2), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first {ns} samples ({ns / 2.4e6:.0f} s) of the same capture, literal C restatement of the "
+                      "reference decode loop (the reference runs it on exactly one thread, src/adsb.rs:147)",
+            "seconds": round(dt, 2),
+            "fast_all_cores": {"value": round(ns / dt_fast / 1e6, 1), "cores": ncores, "kind": "port (optimised, chunk-parallel)"},
+            "gpu_frames_equal_cpu_frames_on_sample": bool(sub.tobytes() == lit.tobytes() and lit.tobytes() == fast.tobytes()),
+            "frames_on_sample": int(len(lit)),
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(world, total),
+            "frames_per_step": state["frames"],
+            "gpu_launches": 3 * args.steps,
+            "kernels_per_step": ["decode_kernel<U8>", "tile_scan_kernel", "gather_kernel"],
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "e2e": e2e,
+            "cpu_baseline": cpu,
+            "hbm_gbs_whole_step": round(alg_bytes / (ms_step * 1e-3) / 1e9, 1) if world == 1 else None,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  The reference is Rust and
+    cannot be built here (no rustc/cargo, no network), so this arm runs the LITERAL C
+    restatement (oracle/adsb_oracle.c) chunk-parallel on every host core, on a bounded
+    sample of the same capture per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from air_rs_b200 import synth
+    from oracle import oracle_c
+
+    ncores = os.cpu_count() or 1
+    ns = REF_SAMPLE
+    table = traffic_table()
+    host = None
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            gen = synth.DeviceSynth(table, device=0)
+            host = gen.render(SEED, 0, ns, synth.FMT_U8, SIGMA, period=PERIOD).cpu().numpy()
+            gen.close()
+    except Exception:
+        host = None
+    if host is None:
+        blocks = [synth.render(table, SEED, j, min(4_000_000, ns - j), synth.FMT_U8, SIGMA, period=PERIOD)
+                  for j in range(0, ns, 4_000_000)]
+        host = np.concatenate(blocks)
+    frames = 0
+    for _ in range(args.warmup):
+        oracle_c.decode_literal_mt(host, threads=ncores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        f, _ = oracle_c.decode_literal_mt(host, threads=ncores)
+        frames = len(f)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = ns / dt / 1e6
+    cfg = workload_config(int(os.environ.get("WORLD_SIZE", 1)), TOTAL_SAMPLES)
+    sample = (f"each step = first {ns} samples ({ns / 2.4e6:.0f} s) of the capture; literal C restatement of the "
+              f"reference (Rust toolchain absent), chunk-parallel on {ncores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg, "frames_per_step": frames,
+        "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3          # timing rule: at least 3 warm-up steps
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

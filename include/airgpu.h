@@ -94,6 +94,8 @@ typedef struct airgpu_stats {
     uint64_t n_tiles;
     float    kernel_ms;      /* device time of the decode kernels (CUDA events), 0 if not measured */
     float    h2d_ms;         /* host->device copy time of the last host-buffer decode   */
+    float    decode_ms;      /* device time of the fused decode kernel alone (last piece) */
+    float    reserved;
 } airgpu_stats;
 
 const char *airgpu_version(void);
