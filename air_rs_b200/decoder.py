@@ -130,7 +130,12 @@ class AdsbDecoder:
         cap = cap or max(4096, n // 256)
         if out is None:
             out = torch.empty((cap, FRAME_DTYPE.itemsize), dtype=torch.uint8, device=iq.device)
-        stream = torch.cuda.current_stream(iq.device).cuda_stream
+        cur = torch.cuda.current_stream(iq.device)
+        stream = cur.cuda_stream
+        if stream == 0:
+            # the legacy default stream is not ordered against the context's own (non-blocking)
+            # compute stream, which NULL selects: make the producer of `iq` finish first
+            cur.synchronize()
         self.decode_device(iq.data_ptr(), n, out.data_ptr(), cap, segment_samples, base_offset, 0, stream)
         return out, self.sync_count()
 

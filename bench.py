@@ -156,7 +156,12 @@ def run_ours(args):
     out = torch.empty((cap, FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     d_count = torch.zeros(1, dtype=torch.int64, device=dev)
     counts_all = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    # a non-default torch stream: the library is handed this stream, so the CUDA events
+    # below are recorded on the very stream the kernels are launched on
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     state = {"frames": 0, "gathered": None}
 
     def decode_resident():
