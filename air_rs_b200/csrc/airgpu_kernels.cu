@@ -60,11 +60,13 @@ constexpr SynTable make_syn()
 __device__ const SynTable g_syn = make_syn();
 
 // ---- shared-memory layout of the level array -------------------------------
-// 16-byte chunks (8 levels).  Phase 1 writes chunk c from lane c (stride 1), phase 2
-// reads chunks 2*lane + t (stride 2).  Swapping odd/even chunks in every second
-// group of 8 makes both patterns bank-conflict free.
+// Each warp owns kWarpLevels u16 levels, in 16-byte chunks (8 levels).  Phase 1 writes
+// chunk c from lane c (stride 1), phase 2 reads chunks 2*lane + t (stride 2).  Flipping
+// bit 3 of the level index whenever bit 6 is set (odd/even chunks swapped in every
+// second group of 8) makes both patterns bank-conflict free, and costs one SHF + one
+// LOP3 for a scalar access.
 __device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 3) & 1); }
-__device__ __forceinline__ int swz_idx(int i) { return (swz_chunk(i >> 3) << 3) | (i & 7); }
+__device__ __forceinline__ int swz_idx(int i) { return i ^ ((i >> 3) & 8); }
 
 // ---- per-sample level -------------------------------------------------------
 // U8: one 32-bit word = (I0, Q0, I1, Q1).  Returns (level0 | level1 << 16).
@@ -93,17 +95,24 @@ __device__ __forceinline__ uint32_t level_cs16(uint32_t w)
 }
 
 template <int FMT>
-struct Fmt;
-template <>
-struct Fmt<AIRGPU_FMT_U8> {
-    static constexpr int kBytesPerSample = 2;
-};
-template <>
-struct Fmt<AIRGPU_FMT_CS16> {
-    static constexpr int kBytesPerSample = 4;
-};
+__device__ __forceinline__ uint4 levels_of_chunk(uint4 a, uint4 b)
+{
+    uint4 o;
+    if (FMT == AIRGPU_FMT_U8) {           // a = 8 samples, b unused
+        o.x = levels_u8_pair(a.x);
+        o.y = levels_u8_pair(a.y);
+        o.z = levels_u8_pair(a.z);
+        o.w = levels_u8_pair(a.w);
+    } else {                              // a, b = 4 samples each
+        o.x = level_cs16(a.x) | (level_cs16(a.y) << 16);
+        o.y = level_cs16(a.z) | (level_cs16(a.w) << 16);
+        o.z = level_cs16(b.x) | (level_cs16(b.y) << 16);
+        o.w = level_cs16(b.z) | (level_cs16(b.w) << 16);
+    }
+    return o;
+}
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+__device__ __forceinline__ uint4 ldg_stream(const void *p)
 {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -112,16 +121,13 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
     return r;
 }
 
-// 16 bytes at byte offset `off` of the tile, zero beyond `avail` bytes or when unaligned.
-__device__ __forceinline__ uint4 load16(const uint8_t *src, long long off, long long avail, bool aligned)
+// 16 bytes at byte offset `off`, zero beyond `avail` bytes; any alignment (edge tiles only).
+__device__ __noinline__ uint4 load16_guarded(const uint8_t *src, long long off, long long avail)
 {
-    if (aligned && off + 16 <= avail)
-        return ldg_stream(reinterpret_cast<const uint4 *>(src + off));
     uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b < 16; ++b)
-        if (off + b < avail)
-            w[b >> 2] |= (uint32_t)src[off + b] << (8 * (b & 3));
+        if (off + b < avail) w[b >> 2] |= (uint32_t)src[off + b] << (8 * (b & 3));
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
@@ -153,46 +159,57 @@ __device__ __forceinline__ bool df17_ok(const uint16_t *s, int i)
 }
 
 struct Cand {
-    uint32_t w[4];   // frame bits, big-endian words (bit 31 of w[0] = frame bit 0)
-    uint32_t fixed;  // 0xFF or repaired bit
+    uint32_t w0, w1, w2, w3;   // frame bits, big-endian words (bit 31 of w0 = frame bit 0)
+    uint32_t fixed;            // 0xFF or repaired bit
     bool valid;
 };
 
-// Warp-cooperative slice + CRC + repair for the candidate at tile offset i
-// (demod.rs:65-82).  All lanes return the same value.
+// Warp-cooperative slice + CRC + repair for the candidate at offset i of the warp's
+// level array (demod.rs:65-82).  All lanes return the same value.
 __device__ __forceinline__ Cand process_candidate(const uint16_t *s, int i, int lane)
 {
     Cand c;
     uint32_t part = 0;
+    uint32_t w[4];
+    uint32_t syn_of[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        int k = 32 * r + lane;
-        bool act = k < 112;
-        int j = i + 16 + 2 * k;
+        const int k = 32 * r + lane;
+        const bool act = (r < 3) || (lane < 16);              // k < 112
+        const int j = i + 16 + 2 * k;
         bool bit = false;
-        if (act) bit = lvl(s, j) < lvl(s, j + 1);   // m[2k] > m[2k+1]  (demod.rs:104)
-        c.w[r] = __brev(__ballot_sync(kFull, bit));
-        if (bit) part ^= __ldg(&g_syn.v[k]);
+        syn_of[r] = act ? __ldg(&g_syn.v[k]) : 0u;
+        if (act) bit = lvl(s, j) < lvl(s, j + 1);              // m[2k] > m[2k+1]  (demod.rs:104)
+        w[r] = __brev(__ballot_sync(kFull, bit));
+        if (bit) part ^= syn_of[r];
     }
-    uint32_t syn = __reduce_xor_sync(kFull, part);
+    const uint32_t syn = __reduce_xor_sync(kFull, part);
     c.fixed = 0xFFu;
     c.valid = true;
     if (syn != 0u) {
         // crc.rs:49-65: only a flip of one of the 88 data bits can match
-        int p = -1;
-        unsigned m0 = __ballot_sync(kFull, __ldg(&g_syn.v[lane]) == syn);
-        unsigned m1 = __ballot_sync(kFull, __ldg(&g_syn.v[32 + lane]) == syn);
-        unsigned m2 = __ballot_sync(kFull, lane < 24 && __ldg(&g_syn.v[64 + lane]) == syn);
-        if (m0) p = __ffs(m0) - 1;
-        else if (m1) p = 32 + __ffs(m1) - 1;
-        else if (m2) p = 64 + __ffs(m2) - 1;
-        if (p < 0) {
-            c.valid = false;
+        const unsigned m0 = __ballot_sync(kFull, syn_of[0] == syn);
+        const unsigned m1 = __ballot_sync(kFull, syn_of[1] == syn);
+        const unsigned m2 = __ballot_sync(kFull, lane < 24 && syn_of[2] == syn);
+        if (m0) {
+            c.fixed = __ffs(m0) - 1;
+            w[0] ^= 0x80000000u >> c.fixed;
+        } else if (m1) {
+            const int q = __ffs(m1) - 1;
+            c.fixed = 32 + q;
+            w[1] ^= 0x80000000u >> q;
+        } else if (m2) {
+            const int q = __ffs(m2) - 1;
+            c.fixed = 64 + q;
+            w[2] ^= 0x80000000u >> q;
         } else {
-            c.w[p >> 5] ^= 0x80000000u >> (p & 31);
-            c.fixed = (uint32_t)p;
+            c.valid = false;
         }
     }
+    c.w0 = w[0];
+    c.w1 = w[1];
+    c.w2 = w[2];
+    c.w3 = w[3];
     return c;
 }
 
@@ -200,94 +217,42 @@ __device__ __forceinline__ Cand process_candidate(const uint16_t *s, int i, int 
 __device__ __forceinline__ unsigned long long record_word(const Cand &c, unsigned long long offset, int which)
 {
     if (which == 0)
-        return (unsigned long long)__byte_perm(c.w[0], 0, 0x0123) |
-               ((unsigned long long)__byte_perm(c.w[1], 0, 0x0123) << 32);
+        return (unsigned long long)__byte_perm(c.w0, 0, 0x0123) |
+               ((unsigned long long)__byte_perm(c.w1, 0, 0x0123) << 32);
     if (which == 1) {
-        uint32_t hi = ((c.w[3] >> 24) & 0xFFu) | (((c.w[3] >> 16) & 0xFFu) << 8) | (c.fixed << 16);
-        return (unsigned long long)__byte_perm(c.w[2], 0, 0x0123) | ((unsigned long long)hi << 32);
+        uint32_t hi = ((c.w3 >> 24) & 0xFFu) | (((c.w3 >> 16) & 0xFFu) << 8) | (c.fixed << 16);
+        return (unsigned long long)__byte_perm(c.w2, 0, 0x0123) | ((unsigned long long)hi << 32);
     }
     return offset;
 }
 
+// Where the frames a warp finds go: pass 0 stages the first kStagePerWarp in shared
+// memory (the output position is not known yet); pass 1, only run when a warp found
+// more than that, writes the rest straight to their final scratch slots.
+struct Sink {
+    unsigned long long *stage;      // [kStagePerWarp][3]
+    unsigned long long *scratch;    // global records, nullptr in pass 0
+    unsigned long long dst0;        // first scratch record of this warp
+    unsigned long long cap;
+    unsigned long long off0;        // frame offset of the warp's candidate 0
+    uint32_t seq;                   // valid frames seen so far in this pass
+    uint32_t gate;                  // gate passes (reference num_processed)
+};
+
+// Gate + slice + CRC over the warp's candidates [0, wcands): the reference's offset
+// loop (adsb.rs:98-114) for this range, emitting in ascending offset order.
 template <int FMT>
-__global__ void __launch_bounds__(kThreads, 3) decode_kernel(const DecodeParams p)
+__device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, int lane, Sink &sink)
 {
-    __shared__ __align__(16) uint16_t s_lvl[kLevels];
-    __shared__ uint32_t s_bits[kBitmapWords];
-    __shared__ unsigned long long s_stage[kWarps][kStagePerWarp][3];
-    __shared__ uint32_t s_cnt[kWarps];
-    __shared__ uint32_t s_pref[kWarps];
-    __shared__ uint32_t s_gate[kWarps];
-    __shared__ unsigned long long s_base;
-
-    constexpr int BPS = Fmt<FMT>::kBytesPerSample;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-
-    const unsigned tile = blockIdx.x;
-    const unsigned long long seg = tile / p.tiles_per_seg;
-    const unsigned long long tile_first = (unsigned long long)(tile % p.tiles_per_seg) * kTile;
-    const unsigned long long seg_start = seg * p.seg_len;
-    const unsigned long long seg_n = min(p.seg_len, p.n_samples - seg_start);
-    const unsigned long long seg_cands = seg_n > (unsigned long long)kFrameSamples ? seg_n - kFrameSamples : 0ull;
-    const int tile_cands = seg_cands > tile_first ? (int)min((unsigned long long)kTile, seg_cands - tile_first) : 0;
-    if (tile_cands == 0) {
-        if (tid == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
-        return;
-    }
-
-    // ---- phase 1: IQ -> inverted levels in shared memory ---------------------
-    {
-        const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + tile_first) * BPS;
-        const long long avail = (long long)(seg_n - tile_first) * BPS;   // bytes to the end of the segment
-        const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-        constexpr int kIter = (kChunks + kThreads - 1) / kThreads;
-        if (FMT == AIRGPU_FMT_U8) {
-            uint4 raw[kIter];
-#pragma unroll
-            for (int k = 0; k < kIter; ++k) {
-                int c = tid + k * kThreads;
-                if (c < kChunks) raw[k] = load16(src, (long long)c * 16, avail, aligned);
-            }
-#pragma unroll
-            for (int k = 0; k < kIter; ++k) {
-                int c = tid + k * kThreads;
-                if (c < kChunks) {
-                    uint4 o;
-                    o.x = levels_u8_pair(raw[k].x);
-                    o.y = levels_u8_pair(raw[k].y);
-                    o.z = levels_u8_pair(raw[k].z);
-                    o.w = levels_u8_pair(raw[k].w);
-                    *reinterpret_cast<uint4 *>(&s_lvl[swz_chunk(c) << 3]) = o;
-                }
-            }
-        } else {
 #pragma unroll 1
-            for (int c = tid; c < kChunks; c += kThreads) {
-                uint4 a = load16(src, (long long)c * 32, avail, aligned);
-                uint4 b = load16(src, (long long)c * 32 + 16, avail, aligned);
-                uint4 o;
-                o.x = level_cs16(a.x) | (level_cs16(a.y) << 16);
-                o.y = level_cs16(a.z) | (level_cs16(a.w) << 16);
-                o.z = level_cs16(b.x) | (level_cs16(b.y) << 16);
-                o.w = level_cs16(b.z) | (level_cs16(b.w) << 16);
-                *reinterpret_cast<uint4 *>(&s_lvl[swz_chunk(c) << 3]) = o;
-            }
-        }
-        s_bits[tid] = 0u;   // kBitmapWords == kThreads
-    }
-    __syncthreads();
-
-    // ---- phase 2: preamble test on packed offset pairs -----------------------
-    // lane owns offsets [ob, ob+16); E[t] = (level[ob+2t], level[ob+2t+1]).
-    for (int it = warp; it * 512 < tile_cands; it += kWarps) {
+    for (int it = 0; it * 512 < wcands; ++it) {
+        // lane owns offsets [ob, ob+16); E[t] = (level[ob+2t], level[ob+2t+1])
         const int ob = it * 512 + lane * 16;
         const int cb = it * 64 + lane * 2;
         uint32_t E[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            uint4 v = *reinterpret_cast<const uint4 *>(&s_lvl[swz_chunk(cb + q) << 3]);
+            const uint4 v = *reinterpret_cast<const uint4 *>(&lv[swz_chunk(cb + q) << 3]);
             E[4 * q + 0] = v.x;
             E[4 * q + 1] = v.y;
             E[4 * q + 2] = v.z;
@@ -303,67 +268,145 @@ __global__ void __launch_bounds__(kThreads, 3) decode_kernel(const DecodeParams 
 #pragma unroll
         for (int t = 5; t < 13; ++t) W[t] = __vimin3_u16x2(ME[t], ME[t + 1], ME[t + 2]);
         // For the offset pair (ob+2t, ob+2t+1):
-        //   highs 0,2,7,9            -> E[t], E[t+1], O[t+3], O[t+4]
+        //   highs 0,2,7,9               -> E[t], E[t+1], O[t+3], O[t+4]
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
         uint32_t D[8];
         uint32_t acc = 0u;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            uint32_t hi = __vmaxu2(__vimax3_u16x2(E[t], E[t + 1], O[t + 3]), O[t + 4]);
-            uint32_t lo = __vimin3_u16x2(__vimin3_u16x2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
+            const uint32_t hi = __vmaxu2(__vimax3_u16x2(E[t], E[t + 1], O[t + 3]), O[t + 4]);
+            const uint32_t lo = __vimin3_u16x2(__vimin3_u16x2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
             D[t] = pass_bits<FMT>(lo, hi);
             acc |= D[t];
         }
-        if (__any_sync(kFull, (acc & 0x80008000u) != 0u)) {
-            if (acc & 0x80008000u) {
-                uint32_t mask = 0u;
+        acc &= 0x80008000u;
+        if (!__any_sync(kFull, acc != 0u)) continue;
+
+        // ---- some lane saw a preamble: DF test per hit, then the survivors ----
+        uint32_t cm = 0u;   // bit o: offset ob + o passes the whole gate
+        if (acc) {
+            uint32_t pm = 0u;   // bit t: offset ob+2t, bit 16+t: offset ob+2t+1
 #pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    mask |= (((D[t] >> 15) & 1u) << (2 * t)) | ((D[t] >> 31) << (2 * t + 1));
-                while (mask) {
-                    int b = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    int i = ob + b;
-                    if (i < tile_cands && df17_ok(s_lvl, i)) atomicOr(&s_bits[i >> 5], 1u << (i & 31));
-                }
+            for (int t = 0; t < 8; ++t) pm |= (D[t] >> (15 - t)) & (0x00010001u << t);
+            while (pm) {
+                const int b = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const int o = 2 * (b & 15) + (b >> 4);
+                if (ob + o < wcands && df17_ok(lv, ob + o)) cm |= 1u << o;
             }
         }
-    }
-    __syncthreads();
-
-    // ---- phase 3: slice + CRC the gate survivors, in offset order per warp ----
-    const unsigned long long off0 = p.base_offset + seg_start + tile_first;
-    const int wi = warp * 32 + lane;
-    uint32_t word = s_bits[wi];
-    uint32_t keep = word;
-    uint32_t nvalid = 0;
-    {
-        uint32_t ngate = __reduce_add_sync(kFull, (uint32_t)__popc(word));
-        if (lane == 0) s_gate[warp] = ngate;
-        unsigned wm = __ballot_sync(kFull, word != 0u);
-        while (wm) {
-            int j = __ffs(wm) - 1;
-            wm &= wm - 1;
-            uint32_t bits = __shfl_sync(kFull, word, j);
+        unsigned lanes = __ballot_sync(kFull, cm != 0u);
+        while (lanes) {
+            const int src_lane = __ffs(lanes) - 1;
+            lanes &= lanes - 1;
+            uint32_t bits = __shfl_sync(kFull, cm, src_lane);
             while (bits) {
-                int b = __ffs(bits) - 1;
+                const int o = __ffs(bits) - 1;
                 bits &= bits - 1;
-                int i = (warp * 32 + j) * 32 + b;
-                Cand c = process_candidate(s_lvl, i, lane);
+                const int i = it * 512 + src_lane * 16 + o;
+                sink.gate += 1;
+                const Cand c = process_candidate(lv, i, lane);
                 if (c.valid) {
-                    if (nvalid < (uint32_t)kStagePerWarp && lane < 3)
-                        s_stage[warp][nvalid][lane] = record_word(c, off0 + (unsigned)i, lane);
-                    nvalid += 1;
-                } else if (lane == j) {
-                    keep &= ~(1u << b);
+                    if (sink.scratch == nullptr) {
+                        if (sink.seq < (uint32_t)kStagePerWarp && lane < 3)
+                            sink.stage[sink.seq * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
+                    } else if (sink.seq >= (uint32_t)kStagePerWarp) {
+                        const unsigned long long rec = sink.dst0 + sink.seq;
+                        if (lane < 3 && rec < sink.cap)
+                            sink.scratch[rec * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
+                    }
+                    sink.seq += 1;
                 }
             }
         }
-        if (lane == 0) s_cnt[warp] = nvalid;
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams p)
+{
+    __shared__ __align__(128) uint16_t s_lvl[kWarps][kWarpLevels];
+    __shared__ unsigned long long s_stage[kWarps][kStagePerWarp * 3];
+    __shared__ uint32_t s_cnt[kWarps];
+    __shared__ uint32_t s_pref[kWarps];
+    __shared__ uint32_t s_gate[kWarps];
+    __shared__ unsigned long long s_base;
+
+    constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
+    constexpr int kChunkBytes = 8 * BPS;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    const unsigned tile = blockIdx.x;
+    const unsigned long long seg = tile / p.tiles_per_seg;
+    const unsigned long long tile_first = (unsigned long long)(tile % p.tiles_per_seg) * kTile;
+    const unsigned long long seg_start = seg * p.seg_len;
+    const unsigned long long seg_n = min(p.seg_len, p.n_samples - seg_start);
+    const unsigned long long seg_cands = seg_n > (unsigned long long)kFrameSamples ? seg_n - kFrameSamples : 0ull;
+    const int tile_cands = seg_cands > tile_first ? (int)min((unsigned long long)kTile, seg_cands - tile_first) : 0;
+
+    // this warp's slice of the tile
+    const int wfirst = warp * kWarpTile;
+    const int wcands = min(max(tile_cands - wfirst, 0), kWarpTile);
+    uint16_t *lv = s_lvl[warp];
+    Sink sink;
+    sink.stage = s_stage[warp];
+    sink.scratch = nullptr;
+    sink.dst0 = 0;
+    sink.cap = p.cap;
+    sink.off0 = p.base_offset + seg_start + tile_first + (unsigned)wfirst;
+    sink.seq = 0;
+    sink.gate = 0;
+
+    if (wcands > 0) {
+        // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
+        const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + tile_first + (unsigned)wfirst) * BPS;
+        const long long avail = (long long)(seg_n - tile_first - (unsigned)wfirst) * BPS;   // bytes to the segment end
+        const bool fast = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && avail >= (long long)kWarpChunks * kChunkBytes;
+        if (fast) {
+            // 9 chunks per lane, three at a time (loads first, then the arithmetic)
+#pragma unroll 1
+            for (int g = 0; g < 3; ++g) {
+                uint4 a[3], b[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int c = lane + 32 * (3 * g + j);
+                    a[j] = ldg_stream(src + c * kChunkBytes);
+                    if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(src + c * kChunkBytes + 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int c = lane + 32 * (3 * g + j);
+                    *reinterpret_cast<uint4 *>(&lv[swz_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j]);
+                }
+            }
+        } else {
+            // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
+            const int need = min(kWarpChunks, (wcands + kFrameSamples + 7) / 8);
+#pragma unroll 1
+            for (int c = lane; c < kWarpChunks; c += 32) {
+                uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+                if (c < need) {
+                    a = load16_guarded(src, (long long)c * kChunkBytes, avail);
+                    if (FMT == AIRGPU_FMT_CS16) b = load16_guarded(src, (long long)c * kChunkBytes + 16, avail);
+                }
+                *reinterpret_cast<uint4 *>(&lv[swz_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b);
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2+3: gate, slice, CRC; first kStagePerWarp frames staged ----
+        scan_warp_range<FMT>(lv, wcands, lane, sink);
+    }
+    const uint32_t nvalid = sink.seq;
+    if (lane == 0) {
+        s_cnt[warp] = nvalid;
+        s_gate[warp] = sink.gate;
     }
     __syncthreads();
 
-    // ---- phase 4: reserve output space once per tile, write the records -------
+    // ---- phase 4: reserve output space once per tile, write the records ----------
     if (tid == 0) {
         uint32_t total = 0, gate = 0;
 #pragma unroll
@@ -384,29 +427,16 @@ __global__ void __launch_bounds__(kThreads, 3) decode_kernel(const DecodeParams 
         unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
         const uint32_t staged = min(nvalid, (uint32_t)kStagePerWarp);
         for (uint32_t q = lane; q < staged * 3; q += 32) {
-            unsigned long long rec = dst0 + q / 3;
-            if (rec < p.cap) scratch[rec * 3 + q % 3] = s_stage[warp][q / 3][q % 3];
+            const unsigned long long rec = dst0 + q / 3;
+            if (rec < p.cap) scratch[rec * 3 + q % 3] = sink.stage[q];
         }
         if (nvalid > (uint32_t)kStagePerWarp) {
-            // rare (dense or degenerate input): recompute the frames that did not fit the stage
-            uint32_t seen = 0;
-            unsigned wm = __ballot_sync(kFull, keep != 0u);
-            while (wm) {
-                int j = __ffs(wm) - 1;
-                wm &= wm - 1;
-                uint32_t bits = __shfl_sync(kFull, keep, j);
-                while (bits) {
-                    int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    if (seen >= (uint32_t)kStagePerWarp) {
-                        int i = (warp * 32 + j) * 32 + b;
-                        Cand c = process_candidate(s_lvl, i, lane);
-                        unsigned long long rec = dst0 + seen;
-                        if (lane < 3 && rec < p.cap) scratch[rec * 3 + lane] = record_word(c, off0 + (unsigned)i, lane);
-                    }
-                    seen += 1;
-                }
-            }
+            // rare (degenerate input such as a constant buffer): second pass over the range
+            sink.scratch = scratch;
+            sink.dst0 = dst0;
+            sink.seq = 0;
+            sink.gate = 0;
+            scan_warp_range<FMT>(lv, wcands, lane, sink);
         }
     }
 }

@@ -14,15 +14,17 @@
 namespace airgpu {
 
 // ---- tiling ---------------------------------------------------------------
-constexpr int kTile = 8192;             // candidate offsets per CTA
-constexpr int kHalo = 256;              // a candidate at i reads samples [i, i+240): 239 needed, 256 keeps 16-byte chunks
-constexpr int kLevels = kTile + kHalo;  // u16 levels staged in shared memory per tile
-constexpr int kChunks = kLevels / 8;    // 16-byte chunks (8 levels each)
+// A warp is the unit of work: it owns kWarpTile consecutive candidate offsets and a
+// private slice of shared memory, so the hot loop has no CTA-wide barrier at all.
+constexpr int kWarpTile = 2048;                   // candidate offsets per warp
+constexpr int kHalo = 256;                        // a candidate at i reads samples [i, i+240): 239 needed, 256 keeps 16-byte chunks
+constexpr int kWarpLevels = kWarpTile + kHalo;    // u16 levels staged per warp
+constexpr int kWarpChunks = kWarpLevels / 8;      // 16-byte chunks (8 levels each): 288 = 9 per lane
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kBitmapWords = kTile / 32;
-constexpr int kStagePerWarp = 16;       // frames a warp can stage before falling back to recompute
-constexpr int kFrameSamples = 240;      // 16 + 112 * 2, reference src/adsb.rs:98
+constexpr int kTile = kWarps * kWarpTile;         // candidate offsets per CTA (one tile_tab entry)
+constexpr int kStagePerWarp = 16;                 // frames a warp stages before falling back to a second pass
+constexpr int kFrameSamples = 240;                // 16 + 112 * 2, reference src/adsb.rs:98
 
 struct DecodeParams {
     const void *iq;                 // interleaved IQ, device memory
