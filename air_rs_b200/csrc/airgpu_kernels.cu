@@ -60,23 +60,27 @@ constexpr SynTable make_syn()
 __device__ const SynTable g_syn = make_syn();
 
 // ---- shared-memory layout of the level array -------------------------------
-// Each warp owns kWarpLevels u16 levels, in 16-byte chunks (8 levels).  Phase 1 writes
-// chunk c from lane c (stride 1), phase 2 reads chunks 2*lane + t (stride 2).  Flipping
-// bit 3 of the level index whenever bit 6 is set (odd/even chunks swapped in every
-// second group of 8) makes both patterns bank-conflict free, and costs one SHF + one
-// LOP3 for a scalar access.
-__device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 3) & 1); }
-__device__ __forceinline__ int swz_idx(int i) { return i ^ ((i >> 3) & 8); }
+// Each warp owns kWarpLevels u16 levels in 16-byte chunks (8 levels).  Phase 1 writes
+// chunk c from lane c (stride 1), phase 2 reads chunks 2*lane + t (stride 2).  One
+// 16-byte pad after every 128 bytes keeps the stride-1 pattern conflict free and leaves
+// a single 2-way conflict in one of the four stride-2 loads; unlike an XOR swizzle it
+// keeps runs of consecutive levels at consecutive addresses, so the scalar readers (DF
+// test, bit slicer) pay the index arithmetic once per run instead of once per level.
+constexpr int kWarpLevelsPadded = kWarpLevels + 8 * (kWarpLevels / 64);
+__device__ __forceinline__ int phys_chunk(int c) { return c + (c >> 3); }
+__device__ __forceinline__ int phys_idx(int i) { return i + ((i >> 6) << 3); }
 
 // ---- per-sample level -------------------------------------------------------
 // U8: one 32-bit word = (I0, Q0, I1, Q1).  Returns (level0 | level1 << 16).
 __device__ __forceinline__ uint32_t levels_u8_pair(uint32_t w)
 {
-    uint32_t n0 = ~w & 0x0000FFFFu;   // (255-I0, 255-Q0, 0, 0)
-    uint32_t n1 = ~w & 0xFFFF0000u;   // (0, 0, 255-I1, 255-Q1)
-    uint32_t z0 = __dp4a(n0, w, 0u);  // I0*(255-I0) + Q0*(255-Q0)  <= 32512
-    uint32_t z1 = __dp4a(n1, w, 0u);
-    return z0 + (z1 << 16);
+    // z = I*(255-I) + Q*(255-Q) <= 32512 per sample.  The integer ALU pipe is the busy
+    // one in this kernel, so the complement is taken as w * -1 + -1 (IMAD, FMA pipe):
+    uint32_t nw;
+    asm("mad.lo.u32 %0, %1, 0xFFFFFFFF, 0xFFFFFFFF;" : "=r"(nw) : "r"(w));   // ~w
+    const uint32_t zsum = __dp4a(nw, w, 0u);                  // z0 + z1
+    const uint32_t z1 = __dp4a(nw, w & 0xFFFF0000u, 0u);      // z1
+    return zsum + z1 * 65535u;                                // z0 + (z1 << 16)
 }
 
 // CS16: one 32-bit word = (re, im) little-endian i16.  Exact floor(sqrt(re^2+im^2)).
@@ -131,30 +135,43 @@ __device__ __noinline__ uint4 load16_guarded(const uint8_t *src, long long off, 
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// bits 15 and 31 of the result: (hi <= lo) per u16 half, i.e. the reference's
-// "no high is below any low" (demod.rs:27-31) in the inverted level domain.
+// bits 15 and 31 of the result are FAIL flags: set iff hi > lo in that u16 half, i.e.
+// the reference's "a high is below a low" (demod.rs:27-31) in the inverted level domain.
 template <int FMT>
-__device__ __forceinline__ uint32_t pass_bits(uint32_t lo, uint32_t hi)
+__device__ __forceinline__ uint32_t fail_bits(uint32_t lo, uint32_t hi)
 {
     if (FMT == AIRGPU_FMT_U8) {
-        // levels < 2^15: (lo + 0x8000 - hi) keeps bit 15 iff lo >= hi, no borrow across halves
-        return lo + 0x80008000u - hi;
+        // U8 levels are <= 0x7F00: read as bf16 they are finite, non-negative and ordered
+        // like the integers, subnormals included, so sign(lo - hi) is the comparison and a
+        // tie gives +0.  One HFMA2.BF16 on the FMA pipe instead of an integer-pipe op.
+        uint32_t d;
+        asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(0xBF80BF80u), "r"(lo));
+        return d;
     } else {
         bool ph, pl;
-        (void)__vibmax_u16x2(lo, hi, &ph, &pl);
-        return (ph ? 0x80000000u : 0u) | (pl ? 0x00008000u : 0u);
+        (void)__vibmax_u16x2(lo, hi, &ph, &pl);          // predicates: lo >= hi
+        return (ph ? 0u : 0x80000000u) | (pl ? 0u : 0x00008000u);
     }
 }
 
-__device__ __forceinline__ uint32_t lvl(const uint16_t *s, int i) { return s[swz_idx(i)]; }
+__device__ __forceinline__ uint32_t lvl(const uint16_t *s, int i) { return s[phys_idx(i)]; }
 
 // DF = 17 test on the first five data bits (demod.rs:45-54), inverted levels.
 __device__ __forceinline__ bool df17_ok(const uint16_t *s, int i)
 {
-    uint32_t hi = max(max(lvl(s, i + 16), lvl(s, i + 19)), max(lvl(s, i + 21), lvl(s, i + 23)));
-    hi = max(hi, lvl(s, i + 24));
-    uint32_t lo = min(min(lvl(s, i + 17), lvl(s, i + 18)), min(lvl(s, i + 20), lvl(s, i + 22)));
-    lo = min(lo, lvl(s, i + 25));
+    const int j = i + 16;
+    const uint16_t *q = s + phys_idx(j);
+    uint32_t v[10];
+    if ((j & 63) <= 54) {                 // levels j..j+9 lie between two pads
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = q[k];
+    } else {
+        const int cross = 64 - (j & 63);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = q[k + (k >= cross ? 8 : 0)];
+    }
+    const uint32_t hi = max(max(max(v[0], v[3]), max(v[5], v[7])), v[8]);
+    const uint32_t lo = min(min(min(v[1], v[2]), min(v[4], v[6])), v[9]);
     return hi <= lo;
 }
 
@@ -252,7 +269,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
         uint32_t E[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(&lv[swz_chunk(cb + q) << 3]);
+            const uint4 v = *reinterpret_cast<const uint4 *>(&lv[phys_chunk(cb + q) << 3]);
             E[4 * q + 0] = v.x;
             E[4 * q + 1] = v.y;
             E[4 * q + 2] = v.z;
@@ -271,15 +288,15 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
         //   highs 0,2,7,9               -> E[t], E[t+1], O[t+3], O[t+4]
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
         uint32_t D[8];
-        uint32_t acc = 0u;
+        uint32_t acc = 0xFFFFFFFFu;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             const uint32_t hi = __vmaxu2(__vimax3_u16x2(E[t], E[t + 1], O[t + 3]), O[t + 4]);
             const uint32_t lo = __vimin3_u16x2(__vimin3_u16x2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
-            D[t] = pass_bits<FMT>(lo, hi);
-            acc |= D[t];
+            D[t] = fail_bits<FMT>(lo, hi);
+            acc &= D[t];
         }
-        acc &= 0x80008000u;
+        acc = ~acc & 0x80008000u;          // a half that did not fail in some pair
         if (!__any_sync(kFull, acc != 0u)) continue;
 
         // ---- some lane saw a preamble: DF test per hit, then the survivors ----
@@ -287,7 +304,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
         if (acc) {
             uint32_t pm = 0u;   // bit t: offset ob+2t, bit 16+t: offset ob+2t+1
 #pragma unroll
-            for (int t = 0; t < 8; ++t) pm |= (D[t] >> (15 - t)) & (0x00010001u << t);
+            for (int t = 0; t < 8; ++t) pm |= (~D[t] >> (15 - t)) & (0x00010001u << t);
             while (pm) {
                 const int b = __ffs(pm) - 1;
                 pm &= pm - 1;
@@ -325,7 +342,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams p)
 {
-    __shared__ __align__(128) uint16_t s_lvl[kWarps][kWarpLevels];
+    __shared__ __align__(128) uint16_t s_lvl[kWarps][kWarpLevelsPadded];
     __shared__ unsigned long long s_stage[kWarps][kStagePerWarp * 3];
     __shared__ uint32_t s_cnt[kWarps];
     __shared__ uint32_t s_pref[kWarps];
@@ -339,9 +356,9 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
     const int warp = tid >> 5;
 
     const unsigned tile = blockIdx.x;
-    const unsigned long long seg = tile / p.tiles_per_seg;
-    const unsigned long long tile_first = (unsigned long long)(tile % p.tiles_per_seg) * kTile;
-    const unsigned long long seg_start = seg * p.seg_len;
+    const unsigned seg = tile / p.tiles_per_seg;                       // 32-bit: n_tiles < 2^31
+    const unsigned long long tile_first = (unsigned long long)(tile - seg * p.tiles_per_seg) * kTile;
+    const unsigned long long seg_start = (unsigned long long)seg * p.seg_len;
     const unsigned long long seg_n = min(p.seg_len, p.n_samples - seg_start);
     const unsigned long long seg_cands = seg_n > (unsigned long long)kFrameSamples ? seg_n - kFrameSamples : 0ull;
     const int tile_cands = seg_cands > tile_first ? (int)min((unsigned long long)kTile, seg_cands - tile_first) : 0;
@@ -378,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int c = lane + 32 * (3 * g + j);
-                    *reinterpret_cast<uint4 *>(&lv[swz_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j]);
+                    *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j]);
                 }
             }
         } else {
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
                     a = load16_guarded(src, (long long)c * kChunkBytes, avail);
                     if (FMT == AIRGPU_FMT_CS16) b = load16_guarded(src, (long long)c * kChunkBytes + 16, avail);
                 }
-                *reinterpret_cast<uint4 *>(&lv[swz_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b);
+                *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b);
             }
         }
         __syncwarp();
