@@ -287,28 +287,34 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
         // For the offset pair (ob+2t, ob+2t+1):
         //   highs 0,2,7,9               -> E[t], E[t+1], O[t+3], O[t+4]
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
-        uint32_t D[8];
-        uint32_t acc = 0xFFFFFFFFu;
+        // F[q] gathers the fail flags of four consecutive offsets (ob+4q .. ob+4q+3) into the
+        // top bits of its four bytes, so the rare path below gets positions almost for free.
+        uint32_t F[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const uint32_t hi = __vmaxu2(__vimax3_u16x2(E[t], E[t + 1], O[t + 3]), O[t + 4]);
-            const uint32_t lo = __vimin3_u16x2(__vimin3_u16x2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
-            D[t] = fail_bits<FMT>(lo, hi);
-            acc &= D[t];
+        for (int q = 0; q < 4; ++q) {
+            uint32_t d[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = 2 * q + h;
+                const uint32_t hi = __vmaxu2(__vimax3_u16x2(E[t], E[t + 1], O[t + 3]), O[t + 4]);
+                const uint32_t lo = __vimin3_u16x2(__vimin3_u16x2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
+                d[h] = fail_bits<FMT>(lo, hi);
+            }
+            F[q] = __byte_perm(d[0], d[1], 0x7351);   // (d0.b1, d0.b3, d1.b1, d1.b3)
         }
-        acc = ~acc & 0x80008000u;          // a half that did not fail in some pair
-        if (!__any_sync(kFull, acc != 0u)) continue;
+        const uint32_t allfail = F[0] & F[1] & F[2] & F[3] & 0x80808080u;
+        if (!__any_sync(kFull, allfail != 0x80808080u)) continue;
 
         // ---- some lane saw a preamble: DF test per hit, then the survivors ----
         uint32_t cm = 0u;   // bit o: offset ob + o passes the whole gate
-        if (acc) {
-            uint32_t pm = 0u;   // bit t: offset ob+2t, bit 16+t: offset ob+2t+1
+        if (allfail != 0x80808080u) {
+            uint32_t pm = 0u;   // bit 8*j + q: offset ob + 4q + j passed the preamble test
 #pragma unroll
-            for (int t = 0; t < 8; ++t) pm |= (~D[t] >> (15 - t)) & (0x00010001u << t);
+            for (int q = 0; q < 4; ++q) pm |= (~F[q] >> (7 - q)) & (0x01010101u << q);
             while (pm) {
                 const int b = __ffs(pm) - 1;
                 pm &= pm - 1;
-                const int o = 2 * (b & 15) + (b >> 4);
+                const int o = 4 * (b & 7) + (b >> 3);
                 if (ob + o < wcands && df17_ok(lv, ob + o)) cm |= 1u << o;
             }
         }
@@ -355,33 +361,36 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
     const int lane = tid & 31;
     const int warp = tid >> 5;
 
+    // Geometry.  `rem` = samples from this warp's first sample to the end of its segment;
+    // everything else follows from it.  The single-segment case (a long capture) avoids the
+    // division; all tile and warp starts are multiples of 2048 samples, so 16-byte alignment
+    // of the loads is a per-launch property (p.vec_ok, computed by the host).
     const unsigned tile = blockIdx.x;
-    const unsigned seg = tile / p.tiles_per_seg;                       // 32-bit: n_tiles < 2^31
-    const unsigned long long tile_first = (unsigned long long)(tile - seg * p.tiles_per_seg) * kTile;
+    unsigned seg = 0, tile_in_seg = tile;
+    if (p.tiles_per_seg < p.n_tiles) {
+        seg = tile / p.tiles_per_seg;
+        tile_in_seg = tile - seg * p.tiles_per_seg;
+    }
     const unsigned long long seg_start = (unsigned long long)seg * p.seg_len;
     const unsigned long long seg_n = min(p.seg_len, p.n_samples - seg_start);
-    const unsigned long long seg_cands = seg_n > (unsigned long long)kFrameSamples ? seg_n - kFrameSamples : 0ull;
-    const int tile_cands = seg_cands > tile_first ? (int)min((unsigned long long)kTile, seg_cands - tile_first) : 0;
-
-    // this warp's slice of the tile
-    const int wfirst = warp * kWarpTile;
-    const int wcands = min(max(tile_cands - wfirst, 0), kWarpTile);
+    const unsigned long long wpos = (unsigned long long)tile_in_seg * kTile + (unsigned)(warp * kWarpTile);
+    const unsigned long long rem = seg_n > wpos ? seg_n - wpos : 0ull;
+    const int wcands = rem > (unsigned long long)kFrameSamples
+                           ? (int)min((unsigned long long)kWarpTile, rem - kFrameSamples) : 0;
     uint16_t *lv = s_lvl[warp];
     Sink sink;
     sink.stage = s_stage[warp];
     sink.scratch = nullptr;
     sink.dst0 = 0;
     sink.cap = p.cap;
-    sink.off0 = p.base_offset + seg_start + tile_first + (unsigned)wfirst;
+    sink.off0 = p.base_offset + seg_start + wpos;
     sink.seq = 0;
     sink.gate = 0;
 
     if (wcands > 0) {
         // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
-        const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + tile_first + (unsigned)wfirst) * BPS;
-        const long long avail = (long long)(seg_n - tile_first - (unsigned)wfirst) * BPS;   // bytes to the segment end
-        const bool fast = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && avail >= (long long)kWarpChunks * kChunkBytes;
-        if (fast) {
+        const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
+        if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
             // 9 chunks per lane, three at a time (loads first, then the arithmetic)
 #pragma unroll 1
             for (int g = 0; g < 3; ++g) {
@@ -400,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
             }
         } else {
             // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
+            const long long avail = (long long)rem * BPS;   // bytes to the end of the segment
             const int need = min(kWarpChunks, (wcands + kFrameSamples + 7) / 8);
 #pragma unroll 1
             for (int c = lane; c < kWarpChunks; c += 32) {
