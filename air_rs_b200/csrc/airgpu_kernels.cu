@@ -300,7 +300,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
                 const uint32_t lo = __vimin3_u16x2(__vimin3_u16x2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
                 d[h] = fail_bits<FMT>(lo, hi);
             }
-            F[q] = __byte_perm(d[0], d[1], 0x7351);   // (d0.b1, d0.b3, d1.b1, d1.b3)
+            F[q] = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
         }
         const uint32_t allfail = F[0] & F[1] & F[2] & F[3] & 0x80808080u;
         if (!__any_sync(kFull, allfail != 0x80808080u)) continue;
