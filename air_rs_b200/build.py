@@ -51,5 +51,25 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+HOST_BIN = LIBDIR / "airgpu_playback"
+
+
+def build_host(force: bool = False) -> Path:
+    """Compile the C++ three-thread harness (csrc/host) against libairgpu.so."""
+    src = CSRC / "host" / "airgpu_playback.cpp"
+    hdr = CSRC / "host" / "adsb_host.hpp"
+    build()
+    stale = (not HOST_BIN.exists()) or HOST_BIN.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime,
+                                                                      LIB.stat().st_mtime)
+    if force or stale:
+        cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-Wall", str(src), "-o", str(HOST_BIN),
+               f"-L{LIBDIR}", "-lairgpu", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_host(force=True))

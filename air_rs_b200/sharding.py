@@ -1,0 +1,70 @@
+"""Long-capture sharding across the GPUs of one node.
+
+A candidate offset i reads samples [i, i+240) and nothing else (reference
+src/adsb.rs:98-106: no state is carried between offsets), so a capture of N
+samples shards naturally: the candidates [0, N-240) are cut into `world`
+contiguous ranges and rank r decodes samples [a_r, b_r + 240) as one segment with
+base_offset = a_r.  Every candidate is owned by exactly one rank; concatenating
+the per-rank frame lists in rank order is the reference's emission order.  The
+only exchange is the all-gather of those lists.
+
+One process per GPU; `torch.distributed` supplies the plumbing (NCCL on GPUs,
+gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+HALO = 240          # samples a candidate reads beyond its own offset, plus one (16 + 112*2)
+ALIGN = 16384       # shard starts on a CTA-tile boundary (keeps 16-byte aligned loads)
+
+RECORD_BYTES = 24   # sizeof(airgpu_frame)
+
+
+def shard_bounds(n_samples: int, world: int, align: int = ALIGN) -> List[int]:
+    """Candidate-range boundaries b[0..world]: rank r owns candidates [b[r], b[r+1])."""
+    cands = max(0, n_samples - HALO)
+    b = [min(cands, (cands * r // world) // align * align) for r in range(world)]
+    b.append(cands)
+    return b
+
+
+def shard_samples(n_samples: int, world: int, rank: int, align: int = ALIGN) -> Tuple[int, int]:
+    """(first sample, number of samples) rank `rank` must hold: its candidates + the halo."""
+    b = shard_bounds(n_samples, world, align)
+    first, last = b[rank], b[rank + 1]
+    if last <= first:
+        return first, 0
+    return first, last - first + HALO
+
+
+def allgather_frames(frames, count, group=None):
+    """All-gather per-rank ordered frame lists.
+
+    frames: uint8 tensor [cap, 24] on this rank's device (first `count` rows valid)
+    count:  int64 tensor [1] on the same device (device-resident count is fine)
+    Returns (slab [world, m, 24], counts [world] on the host) where m = max count;
+    rank r's frames are slab[r, :counts[r]].  Two collectives: counts, then records
+    padded to the largest count.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    counts_dev = torch.empty(world, dtype=torch.int64, device=frames.device)
+    dist.all_gather_into_tensor(counts_dev, count.reshape(1), group=group)
+    counts = counts_dev.cpu()
+    m = int(counts.max())
+    slab = torch.empty((world, max(m, 1), RECORD_BYTES), dtype=torch.uint8, device=frames.device)
+    if m > frames.shape[0]:
+        raise ValueError(f"a rank produced {m} frames but the local buffer holds {frames.shape[0]}")
+    dist.all_gather_into_tensor(slab.view(-1), frames[: max(m, 1)].reshape(-1), group=group)
+    return slab, counts
+
+
+def concat_gathered(slab, counts):
+    """Global ordered frame list [sum(counts), 24] from an all-gathered slab."""
+    import torch
+
+    parts = [slab[r, : int(c)] for r, c in enumerate(counts.tolist())]
+    return torch.cat(parts, dim=0) if parts else slab.new_zeros((0, RECORD_BYTES))

@@ -115,12 +115,6 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def shard_bounds(total: int, n: int):
-    cands = total - HALO
-    b = [(cands * k // n) // 8192 * 8192 for k in range(n)] + [cands]
-    return b
-
-
 def run_ours(args):
     import torch
 
@@ -141,10 +135,10 @@ def run_ours(args):
 
         dist.init_process_group("nccl", device_id=dev)
 
+    from air_rs_b200 import sharding
+
     total = TOTAL_SAMPLES
-    bounds = shard_bounds(total, world)
-    a, b = bounds[rank], bounds[rank + 1]
-    n_local = b - a + HALO                      # candidates [a, b) need samples [a, b + 240)
+    a, n_local = sharding.shard_samples(total, world, rank)   # candidates [a, b) need samples [a, b + 240)
 
     table = traffic_table()
     gen = synth.DeviceSynth(table, device=local)
@@ -155,7 +149,6 @@ def run_ours(args):
     cap = max(1 << 16, int(n_local / 240))      # ~3x the dense-traffic frame density
     out = torch.empty((cap, FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     d_count = torch.zeros(1, dtype=torch.int64, device=dev)
-    counts_all = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
     # a non-default torch stream: the library is handed this stream, so the CUDA events
     # below are recorded on the very stream the kernels are launched on
     tstream = torch.cuda.Stream(device=dev)
@@ -169,11 +162,7 @@ def run_ours(args):
 
     def gather():
         """NCCL all-gather of the per-rank ordered lists (rank order == offset order)."""
-        dist.all_gather_into_tensor(counts_all, d_count)
-        counts = counts_all.cpu()
-        m = int(counts.max())
-        slab = torch.empty((world, m, FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(slab.view(-1), out[:m].reshape(-1))
+        slab, counts = sharding.allgather_frames(out, d_count)
         state["gathered"] = (slab, counts)
         state["frames"] = int(counts.sum())
 

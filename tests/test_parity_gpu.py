@@ -329,3 +329,24 @@ def test_round_trip_clean_frames(dec_u8):
     for s, f in zip(starts, frames):
         r = by_off.get(int(s))
         assert r is not None and bytes(r["bytes"]) == f and r["fixed_bit"] == 0xFF
+
+
+def test_cpp_host_harness_playback(tmp_path):
+    """csrc/host: the C++ mirror of launch_adsb (playback -> decode thread on the C ABI -> display)
+    replays a .c16 file in 20 000-sample buffers and prints the reference's frames in order."""
+    import subprocess
+
+    from air_rs_b200 import build
+
+    exe = build.build_host()
+    _, iq = capture_cs16(seed=91, n=250_000)
+    path = tmp_path / "capture.c16"
+    iq.astype("<i2").tofile(path)                 # SatDump-compatible .c16, utils.rs:7-20
+    r = subprocess.run([str(exe), str(path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("== ")]
+    n = iq.size // 2
+    kept = ((n - 1) // 20_000) * 20_000 if n % 20_000 else n - 20_000   # playback drops the tail (adsb.rs:77)
+    want, _ = oracle_c.decode_fast(iq[: 2 * kept], 20_000, 0, threads=2)
+    assert [ln.split()[1] for ln in lines] == [bytes(f["bytes"]).hex() for f in want]
+    assert len(lines) > 50 and f"packets: {len(want)}" in r.stdout
