@@ -88,7 +88,8 @@ struct airgpu_ctx {
     airgpu_frame *scratch = nullptr;
     size_t scratch_cap = 0;
     uint2 *tile_tab = nullptr;
-    unsigned long long *tile_pos = nullptr;
+    unsigned long long *group_sum = nullptr;   // 2 * groups_cap: sums, then bases
+    size_t groups_cap = 0;
     size_t tiles_cap = 0;
     unsigned long long *counters = nullptr;   // kNumCounters + 1 (last = running frame total)
     unsigned long long *h_counters = nullptr; // pinned mirror
@@ -113,14 +114,16 @@ int ensure_tiles(airgpu_ctx *c, size_t n_tiles)
     if (n_tiles <= c->tiles_cap) return AIRGPU_OK;
     CU(cudaDeviceSynchronize());
     if (c->tile_tab) cudaFree(c->tile_tab);
-    if (c->tile_pos) cudaFree(c->tile_pos);
+    if (c->group_sum) cudaFree(c->group_sum);
     c->tile_tab = nullptr;
-    c->tile_pos = nullptr;
+    c->group_sum = nullptr;
     c->tiles_cap = 0;
     size_t want = std::max<size_t>(n_tiles, 1024);
+    size_t groups = (want + kGroupTiles - 1) / kGroupTiles;
     CU(cudaMalloc(&c->tile_tab, want * sizeof(uint2)));
-    CU(cudaMalloc(&c->tile_pos, want * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->group_sum, 2 * groups * sizeof(unsigned long long)));
     c->tiles_cap = want;
+    c->groups_cap = groups;
     return AIRGPU_OK;
 }
 
@@ -161,8 +164,10 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     if ((rc = ensure_tiles(c, g.n_tiles)) != AIRGPU_OK) return rc;
     if ((rc = ensure_scratch(c, std::max<size_t>(cap, 1))) != AIRGPU_OK) return rc;
 
-    // the scratch index restarts with every piece
+    // the scratch index and the per-group sums restart with every piece
     CU(cudaMemsetAsync(c->counters + kCounterFrames, 0, sizeof(unsigned long long), stream));
+    const size_t n_groups = (g.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    if (n_groups) CU(cudaMemsetAsync(c->group_sum, 0, n_groups * sizeof(unsigned long long), stream));
 
     DecodeParams p{};
     p.iq = d_iq;
@@ -176,11 +181,13 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.cap = cap;
     p.counters = c->counters;
     p.tile_tab = c->tile_tab;
+    p.group_sum = c->group_sum;
+    p.group_base = c->group_sum + c->groups_cap;
     CU(cudaEventRecord(c->evk0, stream));
     CU(launch_decode(c->format, p, stream));
     CU(cudaEventRecord(c->evk1, stream));
     c->evk_valid = true;
-    CU(launch_finalize(p, c->tile_pos, d_out, d_total, stream));
+    CU(launch_finalize(p, d_out, d_total, stream));
     c->stats.n_tiles += g.n_tiles;
     c->stats.n_samples += n;
     return AIRGPU_OK;
@@ -232,7 +239,7 @@ void airgpu_destroy(airgpu_ctx *c)
     }
     if (c->scratch) cudaFree(c->scratch);
     if (c->tile_tab) cudaFree(c->tile_tab);
-    if (c->tile_pos) cudaFree(c->tile_pos);
+    if (c->group_sum) cudaFree(c->group_sum);
     if (c->counters) cudaFree(c->counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->out_dev) cudaFree(c->out_dev);

@@ -443,7 +443,10 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
             gate += s_gate[w];
         }
         unsigned long long base = 0;
-        if (total) base = atomicAdd(&p.counters[kCounterFrames], (unsigned long long)total);
+        if (total) {
+            base = atomicAdd(&p.counters[kCounterFrames], (unsigned long long)total);
+            atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)total);
+        }
         if (gate) atomicAdd(&p.counters[kCounterGate], (unsigned long long)gate);
         s_base = base;
         p.tile_tab[tile] = make_uint2((unsigned)min(base, 0xFFFFFFFFull), total);
@@ -468,63 +471,85 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
     }
 }
 
-// ---- ordering: exclusive scan of the per-tile counts, then gather ---------------
+// ---- ordering: two-level exclusive scan of the per-tile counts, then gather ------
+// decode_kernel already added every tile's count into group_sum[tile / kGroupTiles];
+// group_scan_kernel turns those few sums into bases (one CTA), and gather_kernel re-scans
+// the counts of its own group in shared memory and copies the records to their final,
+// globally ordered position.  Both are tiny next to the decode kernel at any capture size.
 constexpr int kScanThreads = 1024;
 
-__global__ void __launch_bounds__(kScanThreads, 1)
-tile_scan_kernel(const uint2 *tile_tab, unsigned n_tiles, unsigned long long *tile_pos,
-                 unsigned long long *d_count)
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long *s_warp,
+                                                                   unsigned long long *total)
 {
-    __shared__ unsigned long long s_warp[kScanThreads / 32];
-    __shared__ unsigned long long s_running;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_running = *d_count;   // frames already in `out` (pieces of one call append)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(kFull, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    for (unsigned base = 0; base < n_tiles; base += kScanThreads) {
-        unsigned t = base + tid;
-        unsigned long long v = t < n_tiles ? tile_tab[t].y : 0u;
-        unsigned long long x = v;
+    if (warp == 0) {
+        const unsigned long long wsum = lane < nwarps ? s_warp[lane] : 0ull;
+        unsigned long long y = wsum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long y = __shfl_up_sync(kFull, x, d);
-            if (lane >= d) x += y;
+            const unsigned long long z = __shfl_up_sync(kFull, y, d);
+            if (lane >= d) y += z;
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long wsum = s_warp[lane];
-            unsigned long long y = wsum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned long long z = __shfl_up_sync(kFull, y, d);
-                if (lane >= d) y += z;
-            }
-            s_warp[lane] = y - wsum;   // exclusive prefix of the warp sums
-        }
-        __syncthreads();
-        unsigned long long run = s_running;
-        unsigned long long incl = run + s_warp[warp] + x;
-        if (t < n_tiles) tile_pos[t] = incl - v;
-        __syncthreads();
-        if (tid == kScanThreads - 1) s_running = incl;
+        if (lane < nwarps) s_warp[lane] = y - wsum;
+        if (lane == 31) s_warp[32] = y;
     }
     __syncthreads();
-    if (tid == 0) *d_count = s_running;
+    const unsigned long long excl = s_warp[warp] + x - v;
+    *total = s_warp[32];
+    __syncthreads();
+    return excl;
 }
 
-__global__ void __launch_bounds__(256)
-gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const unsigned long long *tile_pos,
+__global__ void __launch_bounds__(kScanThreads, 1)
+group_scan_kernel(const unsigned long long *group_sum, unsigned n_groups, unsigned long long *group_base,
+                  unsigned long long *d_total)
+{
+    __shared__ unsigned long long s_warp[33];
+    unsigned long long running = *d_total;   // frames already in `out` (pieces of one call append)
+    for (unsigned base = 0; base < n_groups; base += kScanThreads) {
+        const unsigned g = base + threadIdx.x;
+        const unsigned long long v = g < n_groups ? group_sum[g] : 0ull;
+        unsigned long long total;
+        const unsigned long long excl = block_exclusive_scan(v, s_warp, &total);
+        if (g < n_groups) group_base[g] = running + excl;
+        running += total;
+    }
+    if (threadIdx.x == 0) *d_total = running;
+}
+
+__global__ void __launch_bounds__(kGroupTiles)
+gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const unsigned long long *group_base,
               unsigned n_tiles, unsigned long long *out, unsigned long long cap)
 {
-    const unsigned t = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (t >= n_tiles) return;
-    const uint2 e = tile_tab[t];
-    if (e.y == 0) return;
-    const unsigned long long pos = tile_pos[t];
-    for (unsigned q = lane; q < e.y * 3; q += 32) {
-        unsigned long long src = (unsigned long long)e.x + q / 3, dst = pos + q / 3;
-        if (src < cap && dst < cap) out[dst * 3 + q % 3] = scratch[src * 3 + q % 3];
+    __shared__ unsigned long long s_warp[33];
+    __shared__ unsigned long long s_pos[kGroupTiles];
+    __shared__ uint2 s_tab[kGroupTiles];
+    const unsigned t0 = blockIdx.x * kGroupTiles;
+    const unsigned t = t0 + threadIdx.x;
+    const uint2 e = t < n_tiles ? tile_tab[t] : make_uint2(0u, 0u);
+    unsigned long long total;
+    const unsigned long long excl = block_exclusive_scan(e.y, s_warp, &total);
+    if (total == 0) return;
+    s_pos[threadIdx.x] = group_base[blockIdx.x] + excl;
+    s_tab[threadIdx.x] = e;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int k = warp; k < kGroupTiles; k += nwarps) {
+        const uint2 ek = s_tab[k];
+        if (ek.y == 0) continue;
+        const unsigned long long pos = s_pos[k];
+        for (unsigned q = lane; q < ek.y * 3; q += 32) {
+            const unsigned long long src = (unsigned long long)ek.x + q / 3, dst = pos + q / 3;
+            if (src < cap && dst < cap) out[dst * 3 + q % 3] = scratch[src * 3 + q % 3];
+        }
     }
 }
 
@@ -552,16 +577,17 @@ cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream
     return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const DecodeParams &p, unsigned long long *tile_pos, airgpu_frame *out,
-                            unsigned long long *d_count, cudaStream_t stream)
+cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned long long *d_total,
+                            cudaStream_t stream)
 {
-    tile_scan_kernel<<<1, kScanThreads, 0, stream>>>(p.tile_tab, p.n_tiles, tile_pos, d_count);
+    const unsigned n_groups = (p.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    group_scan_kernel<<<1, kScanThreads, 0, stream>>>(p.group_sum, n_groups, p.group_base, d_total);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (p.n_tiles == 0) return cudaSuccess;
-    gather_kernel<<<(p.n_tiles + 7) / 8, 256, 0, stream>>>(
-        reinterpret_cast<const unsigned long long *>(p.scratch), p.tile_tab, tile_pos, p.n_tiles,
-        reinterpret_cast<unsigned long long *>(out), p.cap);
+    if (n_groups == 0) return cudaSuccess;
+    gather_kernel<<<n_groups, kGroupTiles, 0, stream>>>(reinterpret_cast<const unsigned long long *>(p.scratch),
+                                                        p.tile_tab, p.group_base, p.n_tiles,
+                                                        reinterpret_cast<unsigned long long *>(out), p.cap);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kTile = kWarps * kWarpTile;         // candidate offsets per CTA (one tile_tab entry)
 constexpr int kStagePerWarp = 16;                 // frames a warp stages before falling back to a second pass
 constexpr int kFrameSamples = 240;                // 16 + 112 * 2, reference src/adsb.rs:98
+constexpr int kGroupTiles = 256;                  // tiles per ordering group (one gather CTA)
 
 struct DecodeParams {
     const void *iq;                 // interleaved IQ, device memory
@@ -38,6 +39,8 @@ struct DecodeParams {
     unsigned long long cap;         // capacity of scratch (and of the final output)
     unsigned long long *counters;   // [0] frames, [1] gate passes, [2] preamble passes
     uint2 *tile_tab;                // per tile: (base index into scratch, frame count)
+    unsigned long long *group_sum;  // per group of kGroupTiles tiles: frames (zeroed before the launch)
+    unsigned long long *group_base; // per group: ordered position of its first frame
 };
 
 enum { kCounterFrames = 0, kCounterGate = 1, kCounterPreamble = 2, kNumCounters = 4 };
@@ -45,8 +48,8 @@ enum { kCounterFrames = 0, kCounterGate = 1, kCounterPreamble = 2, kNumCounters 
 // Launchers (stream-ordered, no synchronisation inside).
 cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream);
 // Ordered frames are appended to `out` at index *d_total (device counter, updated in place).
-cudaError_t launch_finalize(const DecodeParams &p, unsigned long long *tile_pos, airgpu_frame *out,
-                            unsigned long long *d_total, cudaStream_t stream);
+cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned long long *d_total,
+                            cudaStream_t stream);
 
 // Exhaustive self-check helper used by the tests: level (inverted magnitude proxy)
 // the kernel computes for every U8 (I, Q) pair / for a list of CS16 samples.

@@ -312,7 +312,7 @@ def run_ours(args):
             "config": workload_config(world, total),
             "frames_per_step": state["frames"],
             "gpu_launches": 3 * args.steps,
-            "kernels_per_step": ["decode_kernel<U8>", "tile_scan_kernel", "gather_kernel"],
+            "kernels_per_step": ["decode_kernel<U8>", "group_scan_kernel", "gather_kernel"],
             "clocks": sampler.summary(),
             "roofline": roofline,
             "e2e": e2e,
