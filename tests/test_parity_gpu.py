@@ -350,3 +350,24 @@ def test_cpp_host_harness_playback(tmp_path):
     want, _ = oracle_c.decode_fast(iq[: 2 * kept], 20_000, 0, threads=2)
     assert [ln.split()[1] for ln in lines] == [bytes(f["bytes"]).hex() for f in want]
     assert len(lines) > 50 and f"packets: {len(want)}" in r.stdout
+
+
+def test_pipelined_sub_shards_equal_single_pass(dec_u8):
+    """sharding.ShardedDecoder (world 1): four sub-shards decoded back to back == one pass."""
+    import torch
+
+    from air_rs_b200 import sharding
+
+    dev = synth.DeviceSynth(synth.make_traffic(83, 2_400_000, df17_per_s=3000, decoy_per_s=3000, snr_db=(8, 30)))
+    n = 6_000_000
+    t = dev.render(83, 0, n, FMT_U8, 2.0, period=2_400_000)
+    out, count = dec_u8.decode_tensor(t, cap=1 << 17, base_offset=5_000)
+    whole = AdsbDecoder.frames_from_tensor(out, count)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        sd = sharding.ShardedDecoder(dec_u8, n, 5_000, pieces=4)
+        frames, total = sd.step(t)
+        s.synchronize()
+    got = frames.cpu().numpy().view(FRAME_DTYPE).reshape(-1)
+    assert total == len(whole) and frames_equal(got, whole), describe_diff(got, whole)
+    dev.close()
