@@ -99,7 +99,8 @@ class ShardedDecoder:
         self.cap = cap
         self.out = [torch.empty((cap, RECORD_BYTES), dtype=torch.uint8, device=self.dev) for _ in self.ranges]
         self.cnt = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in self.ranges]
-        self.comm = torch.cuda.Stream(device=self.dev)
+        # high priority: NCCL's few CTAs must get SM slots while the decode kernel still has CTAs queued
+        self.comm = torch.cuda.Stream(device=self.dev, priority=-1)
         self.events = [torch.cuda.Event() for _ in self.ranges]
 
     def step(self, iq, bytes_per_sample: int = 2, concat: bool = True):
