@@ -156,7 +156,7 @@ def run_ours(args):
     stream = tstream.cuda_stream
     assert stream != 0
     state = {"frames": 0, "gathered": None}
-    pieces = 1 if world == 1 else int(os.environ.get("AIRGPU_PIECES", 4))
+    pieces = 1 if world == 1 else int(os.environ.get("AIRGPU_PIECES", 2))
     sharded = sharding.ShardedDecoder(dec, n_local, a, pieces=pieces) if world > 1 else None
 
     def decode_resident():
@@ -172,10 +172,9 @@ def run_ours(args):
         if world == 1:
             decode_resident()
         else:
-            # sub-shards decoded back to back; each one's all-gather overlaps the next decode
-            frames, total = sharded.step(iq)
-            state["gathered"] = frames
-            state["frames"] = total
+            # sub-shards decoded back to back; each one's all-gather overlaps the next decode;
+            # no host synchronisation inside a step (sharding.ShardedDecoder)
+            sharded.step(iq)
 
     def barrier():
         if world > 1:
@@ -185,6 +184,8 @@ def run_ours(args):
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
+            if sharded is not None and fn is step:
+                state["gathered"], state["frames"] = sharded.finish()   # also sizes the exchange slabs
         barrier()
         if sampler:
             sampler.active.set()
@@ -192,10 +193,14 @@ def run_ours(args):
         e0.record()
         for _ in range(steps):
             fn()
+        if sharded is not None and fn is step:
+            tstream.wait_stream(sharded.comm)     # the step ends when the last all-gather has landed
         e1.record()
         torch.cuda.synchronize()
         if sampler:
             sampler.active.clear()
+        if sharded is not None and fn is step:
+            state["gathered"], state["frames"] = sharded.finish()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         barrier()
         if world > 1:
@@ -207,6 +212,8 @@ def run_ours(args):
     ms_total = timed(step, args.steps, args.warmup, sampler)
     sampler.stop()
     ms_step = ms_total / args.steps
+    if world > 1:
+        decode_resident()                       # whole local shard once more, for the per-rank frame count
     n_frames_local = int(d_count.item())
     if world == 1:
         state["frames"] = n_frames_local

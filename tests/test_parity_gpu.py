@@ -366,8 +366,17 @@ def test_pipelined_sub_shards_equal_single_pass(dec_u8):
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         sd = sharding.ShardedDecoder(dec_u8, n, 5_000, pieces=4)
-        frames, total = sd.step(t)
-        s.synchronize()
+        sd.step(t)
+        frames, total = sd.finish()          # first step: full-capacity slabs, then sized to the traffic
+        sd.step(t)
+        sd.step(t)
+        frames2, total2 = sd.finish()        # steady state: optimistic slabs, no host sync between steps
+        assert total2 == total and torch.equal(frames, frames2)
+        sd.slab = 16                         # force the "slab too small" path
+        sd._alloc()
+        sd.step(t)
+        frames3, total3 = sd.finish()
+        assert total3 == total and torch.equal(frames, frames3)
     got = frames.cpu().numpy().view(FRAME_DTYPE).reshape(-1)
     assert total == len(whole) and frames_equal(got, whole), describe_diff(got, whole)
     dev.close()
