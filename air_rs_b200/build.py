@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
-LIB = LIBDIR / "libairgpu.so"
+LIB = LIBDIR / os.environ.get("AIRGPU_LIB", "libairgpu.so")   # AIRGPU_LIB: A/B-test a prebuilt variant
 
 SOURCES = ["airgpu_kernels.cu", "airgpu_api.cu", "airgpu_synth.cu"]
 NVCC_FLAGS = [
@@ -36,7 +36,7 @@ def is_stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source into air_rs_b200/_lib/libairgpu.so."""
-    if not force and not is_stale():
+    if (not force and not is_stale()) or "AIRGPU_LIB" in os.environ:
         return LIB
     LIBDIR.mkdir(exist_ok=True)
     srcs = [str(CSRC / s) for s in SOURCES]

@@ -243,6 +243,26 @@ __device__ __forceinline__ unsigned long long record_word(const Cand &c, unsigne
     return offset;
 }
 
+// ptxas maps the 3-input forms to VIMNMX3.U16x2 (64 lanes/clk/SM); the 2-input VIMNMX.U16x2
+// issues at twice that rate when it is not interleaved with VIMNMX3 (tools/ubench2.cu).
+#ifdef AIRGPU_MINMAX2
+__device__ __forceinline__ uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t t = __vminu2(a, b);
+    asm("" : "+r"(t));   // keep the compiler from fusing the pair back into VIMNMX3
+    return __vminu2(t, c);
+}
+__device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t t = __vmaxu2(a, b);
+    asm("" : "+r"(t));
+    return __vmaxu2(t, c);
+}
+#else
+__device__ __forceinline__ uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+#endif
+
 // Where the frames a warp finds go: pass 0 stages the first kStagePerWarp in shared
 // memory (the output position is not known yet); pass 1, only run when a warp found
 // more than that, writes the rest straight to their final scratch slots.
@@ -283,7 +303,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
 #pragma unroll
         for (int t = 1; t < 10; ++t) MO[t] = __vminu2(O[t], E[t + 1]);
 #pragma unroll
-        for (int t = 5; t < 13; ++t) W[t] = __vimin3_u16x2(ME[t], ME[t + 1], ME[t + 2]);
+        for (int t = 5; t < 13; ++t) W[t] = min3u2(ME[t], ME[t + 1], ME[t + 2]);
         // For the offset pair (ob+2t, ob+2t+1):
         //   highs 0,2,7,9               -> E[t], E[t+1], O[t+3], O[t+4]
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
@@ -296,8 +316,8 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int t = 2 * q + h;
-                const uint32_t hi = __vmaxu2(__vimax3_u16x2(E[t], E[t + 1], O[t + 3]), O[t + 4]);
-                const uint32_t lo = __vimin3_u16x2(__vimin3_u16x2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
+                const uint32_t hi = __vmaxu2(max3u2(E[t], E[t + 1], O[t + 3]), O[t + 4]);
+                const uint32_t lo = min3u2(min3u2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
                 d[h] = fail_bits<FMT>(lo, hi);
             }
             F[q] = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
