@@ -246,20 +246,28 @@ __device__ __forceinline__ unsigned long long record_word(const Cand &c, unsigne
 // ptxas maps the 3-input forms to VIMNMX3.U16x2 (64 lanes/clk/SM); the 2-input VIMNMX.U16x2
 // issues at twice that rate when it is not interleaved with VIMNMX3 (tools/ubench2.cu).
 #ifdef AIRGPU_MINMAX2
+// U8 levels are valid, ordered bf16 bit patterns, so the second step can be HMNMX2.BF16,
+// which ptxas cannot fuse with the integer VIMNMX back into a (half-rate) VIMNMX3.
+template <int FMT>
 __device__ __forceinline__ uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c)
 {
-    uint32_t t = __vminu2(a, b);
-    asm("" : "+r"(t));   // keep the compiler from fusing the pair back into VIMNMX3
-    return __vminu2(t, c);
+    if (FMT != AIRGPU_FMT_U8) return __vimin3_u16x2(a, b, c);
+    uint32_t r;
+    asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(__vminu2(a, b)), "r"(c));
+    return r;
 }
+template <int FMT>
 __device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c)
 {
-    uint32_t t = __vmaxu2(a, b);
-    asm("" : "+r"(t));
-    return __vmaxu2(t, c);
+    if (FMT != AIRGPU_FMT_U8) return __vimax3_u16x2(a, b, c);
+    uint32_t r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(__vmaxu2(a, b)), "r"(c));
+    return r;
 }
 #else
+template <int FMT>
 __device__ __forceinline__ uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+template <int FMT>
 __device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
 #endif
 
@@ -303,7 +311,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
 #pragma unroll
         for (int t = 1; t < 10; ++t) MO[t] = __vminu2(O[t], E[t + 1]);
 #pragma unroll
-        for (int t = 5; t < 13; ++t) W[t] = min3u2(ME[t], ME[t + 1], ME[t + 2]);
+        for (int t = 5; t < 13; ++t) W[t] = min3u2<FMT>(ME[t], ME[t + 1], ME[t + 2]);
         // For the offset pair (ob+2t, ob+2t+1):
         //   highs 0,2,7,9               -> E[t], E[t+1], O[t+3], O[t+4]
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
@@ -316,8 +324,8 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int t = 2 * q + h;
-                const uint32_t hi = __vmaxu2(max3u2(E[t], E[t + 1], O[t + 3]), O[t + 4]);
-                const uint32_t lo = min3u2(min3u2(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
+                const uint32_t hi = __vmaxu2(max3u2<FMT>(E[t], E[t + 1], O[t + 3]), O[t + 4]);
+                const uint32_t lo = min3u2<FMT>(min3u2<FMT>(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
                 d[h] = fail_bits<FMT>(lo, hi);
             }
             F[q] = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
