@@ -243,33 +243,13 @@ __device__ __forceinline__ unsigned long long record_word(const Cand &c, unsigne
     return offset;
 }
 
-// ptxas maps the 3-input forms to VIMNMX3.U16x2 (64 lanes/clk/SM); the 2-input VIMNMX.U16x2
-// issues at twice that rate when it is not interleaved with VIMNMX3 (tools/ubench2.cu).
-#ifdef AIRGPU_MINMAX2
-// U8 levels are valid, ordered bf16 bit patterns, so the second step can be HMNMX2.BF16,
-// which ptxas cannot fuse with the integer VIMNMX back into a (half-rate) VIMNMX3.
-template <int FMT>
-__device__ __forceinline__ uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c)
-{
-    if (FMT != AIRGPU_FMT_U8) return __vimin3_u16x2(a, b, c);
-    uint32_t r;
-    asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(__vminu2(a, b)), "r"(c));
-    return r;
-}
-template <int FMT>
-__device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c)
-{
-    if (FMT != AIRGPU_FMT_U8) return __vimax3_u16x2(a, b, c);
-    uint32_t r;
-    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(__vmaxu2(a, b)), "r"(c));
-    return r;
-}
-#else
+// 3-input packed min/max: VIMNMX3.U16x2 (64 lanes/clk/SM).  Splitting them into 2-input
+// VIMNMX.U16x2 + HMNMX2.BF16 pairs (each 128 lanes/clk/SM when issued alone) was measured
+// SLOWER in this mix: 0.903 ms vs 0.807 ms per 960 M samples.
 template <int FMT>
 __device__ __forceinline__ uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 template <int FMT>
 __device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
-#endif
 
 // Where the frames a warp finds go: pass 0 stages the first kStagePerWarp in shared
 // memory (the output position is not known yet); pass 1, only run when a warp found
@@ -419,20 +399,34 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
         // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
         const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
         if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
-            // 9 chunks per lane, three at a time (loads first, then the arithmetic)
-#pragma unroll 1
-            for (int g = 0; g < 3; ++g) {
-                uint4 a[3], b[3];
+            // 9 chunks per lane in three batches; the loads of batch g+1 are in flight while
+            // batch g is converted, so a warp waits for HBM once per tile, not three times
+            uint4 a[3], b[3], na[3], nb[3];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int c = lane + 32 * (3 * g + j);
-                    a[j] = ldg_stream(src + c * kChunkBytes);
-                    if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(src + c * kChunkBytes + 16);
+            for (int j = 0; j < 3; ++j) {
+                const int c = lane + 32 * j;
+                a[j] = ldg_stream(src + c * kChunkBytes);
+                if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(src + c * kChunkBytes + 16);
+            }
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                if (g < 2) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int c = lane + 32 * (3 * (g + 1) + j);
+                        na[j] = ldg_stream(src + c * kChunkBytes);
+                        if (FMT == AIRGPU_FMT_CS16) nb[j] = ldg_stream(src + c * kChunkBytes + 16);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int c = lane + 32 * (3 * g + j);
                     *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    a[j] = na[j];
+                    b[j] = nb[j];
                 }
             }
         } else {
