@@ -354,26 +354,25 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams p)
+__global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams p)
 {
+    // Warps never talk to each other: each owns one tile (kWarpTile candidate offsets), a
+    // private slice of shared memory, its own stage and its own output reservation.  The CTA
+    // is only a packaging unit (4 warps keep the per-CTA footprint small: 8 CTAs per SM).
     __shared__ __align__(128) uint16_t s_lvl[kWarps][kWarpLevelsPadded];
     __shared__ unsigned long long s_stage[kWarps][kStagePerWarp * 3];
-    __shared__ uint32_t s_cnt[kWarps];
-    __shared__ uint32_t s_pref[kWarps];
-    __shared__ uint32_t s_gate[kWarps];
-    __shared__ unsigned long long s_base;
 
     constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
     constexpr int kChunkBytes = 8 * BPS;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
 
     // Geometry.  `rem` = samples from this warp's first sample to the end of its segment;
     // everything else follows from it.  The single-segment case (a long capture) avoids the
-    // division; all tile and warp starts are multiples of 2048 samples, so 16-byte alignment
-    // of the loads is a per-launch property (p.vec_ok, computed by the host).
-    const unsigned tile = blockIdx.x;
+    // division; all tile starts are multiples of 2048 samples, so 16-byte alignment of the
+    // loads is a per-launch property (p.vec_ok, computed by the host).
+    const unsigned tile = blockIdx.x * kWarps + warp;
+    if (tile >= p.n_tiles) return;
     unsigned seg = 0, tile_in_seg = tile;
     if (p.tiles_per_seg < p.n_tiles) {
         seg = tile / p.tiles_per_seg;
@@ -381,10 +380,14 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
     }
     const unsigned long long seg_start = (unsigned long long)seg * p.seg_len;
     const unsigned long long seg_n = min(p.seg_len, p.n_samples - seg_start);
-    const unsigned long long wpos = (unsigned long long)tile_in_seg * kTile + (unsigned)(warp * kWarpTile);
+    const unsigned long long wpos = (unsigned long long)tile_in_seg * kWarpTile;
     const unsigned long long rem = seg_n > wpos ? seg_n - wpos : 0ull;
     const int wcands = rem > (unsigned long long)kFrameSamples
                            ? (int)min((unsigned long long)kWarpTile, rem - kFrameSamples) : 0;
+    if (wcands == 0) {
+        if (lane == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
+        return;
+    }
     uint16_t *lv = s_lvl[warp];
     Sink sink;
     sink.stage = s_stage[warp];
@@ -395,101 +398,85 @@ __global__ void __launch_bounds__(kThreads, 4) decode_kernel(const DecodeParams 
     sink.seq = 0;
     sink.gate = 0;
 
-    if (wcands > 0) {
-        // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
-        const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
-        if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
-            // 9 chunks per lane in three batches; the loads of batch g+1 are in flight while
-            // batch g is converted, so a warp waits for HBM once per tile, not three times
-            uint4 a[3], b[3], na[3], nb[3];
+    // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
+    const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
+    if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
+        // 9 chunks per lane in three batches; the loads of batch g+1 are in flight while
+        // batch g is converted, so a warp waits for HBM once per tile, not three times
+        uint4 a[3], b[3], na[3], nb[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = lane + 32 * j;
+            a[j] = ldg_stream(src + c * kChunkBytes);
+            if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(src + c * kChunkBytes + 16);
+        }
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            if (g < 2) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int c = lane + 32 * (3 * (g + 1) + j);
+                    na[j] = ldg_stream(src + c * kChunkBytes);
+                    if (FMT == AIRGPU_FMT_CS16) nb[j] = ldg_stream(src + c * kChunkBytes + 16);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const int c = lane + 32 * j;
-                a[j] = ldg_stream(src + c * kChunkBytes);
-                if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(src + c * kChunkBytes + 16);
+                const int c = lane + 32 * (3 * g + j);
+                *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j]);
             }
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                if (g < 2) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const int c = lane + 32 * (3 * (g + 1) + j);
-                        na[j] = ldg_stream(src + c * kChunkBytes);
-                        if (FMT == AIRGPU_FMT_CS16) nb[j] = ldg_stream(src + c * kChunkBytes + 16);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int c = lane + 32 * (3 * g + j);
-                    *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    a[j] = na[j];
-                    b[j] = nb[j];
-                }
+            for (int j = 0; j < 3; ++j) {
+                a[j] = na[j];
+                b[j] = nb[j];
             }
-        } else {
-            // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
-            const long long avail = (long long)rem * BPS;   // bytes to the end of the segment
-            const int need = min(kWarpChunks, (wcands + kFrameSamples + 7) / 8);
+        }
+    } else {
+        // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
+        const long long avail = (long long)rem * BPS;   // bytes to the end of the segment
+        const int need = min(kWarpChunks, (wcands + kFrameSamples + 7) / 8);
 #pragma unroll 1
-            for (int c = lane; c < kWarpChunks; c += 32) {
-                uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-                if (c < need) {
-                    a = load16_guarded(src, (long long)c * kChunkBytes, avail);
-                    if (FMT == AIRGPU_FMT_CS16) b = load16_guarded(src, (long long)c * kChunkBytes + 16, avail);
-                }
-                *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b);
+        for (int c = lane; c < kWarpChunks; c += 32) {
+            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+            if (c < need) {
+                a = load16_guarded(src, (long long)c * kChunkBytes, avail);
+                if (FMT == AIRGPU_FMT_CS16) b = load16_guarded(src, (long long)c * kChunkBytes + 16, avail);
             }
+            *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b);
         }
-        __syncwarp();
-
-        // ---- phase 2+3: gate, slice, CRC; first kStagePerWarp frames staged ----
-        scan_warp_range<FMT>(lv, wcands, lane, sink);
     }
+    __syncwarp();
+
+    // ---- phase 2+3: gate, slice, CRC; first kStagePerWarp frames staged ----
+    scan_warp_range<FMT>(lv, wcands, lane, sink);
     const uint32_t nvalid = sink.seq;
-    if (lane == 0) {
-        s_cnt[warp] = nvalid;
-        s_gate[warp] = sink.gate;
-    }
-    __syncthreads();
 
-    // ---- phase 4: reserve output space once per tile, write the records ----------
-    if (tid == 0) {
-        uint32_t total = 0, gate = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            s_pref[w] = total;
-            total += s_cnt[w];
-            gate += s_gate[w];
+    // ---- phase 4: this warp reserves its own output space and writes its records ----
+    unsigned long long base = 0;
+    if (lane == 0) {
+        if (nvalid) {
+            base = atomicAdd(&p.counters[kCounterFrames], (unsigned long long)nvalid);
+            atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)nvalid);
         }
-        unsigned long long base = 0;
-        if (total) {
-            base = atomicAdd(&p.counters[kCounterFrames], (unsigned long long)total);
-            atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)total);
-        }
-        if (gate) atomicAdd(&p.counters[kCounterGate], (unsigned long long)gate);
-        s_base = base;
-        p.tile_tab[tile] = make_uint2((unsigned)min(base, 0xFFFFFFFFull), total);
+        if (sink.gate) atomicAdd(&p.counters[kCounterGate], (unsigned long long)sink.gate);
+        p.tile_tab[tile] = make_uint2((unsigned)min(base, 0xFFFFFFFFull), nvalid);
     }
-    __syncthreads();
-    if (nvalid) {
-        const unsigned long long dst0 = s_base + s_pref[warp];
-        unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
-        const uint32_t staged = min(nvalid, (uint32_t)kStagePerWarp);
-        for (uint32_t q = lane; q < staged * 3; q += 32) {
-            const unsigned long long rec = dst0 + q / 3;
-            if (rec < p.cap) scratch[rec * 3 + q % 3] = sink.stage[q];
-        }
-        if (nvalid > (uint32_t)kStagePerWarp) {
-            // rare (degenerate input such as a constant buffer): second pass over the range
-            sink.scratch = scratch;
-            sink.dst0 = dst0;
-            sink.seq = 0;
-            sink.gate = 0;
-            scan_warp_range<FMT>(lv, wcands, lane, sink);
-        }
+    if (nvalid == 0) return;
+    base = __shfl_sync(kFull, base, 0);
+    __syncwarp();                                    // stage writes (lanes 0..2) visible to the warp
+    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
+    const uint32_t staged = min(nvalid, (uint32_t)kStagePerWarp);
+    for (uint32_t q = lane; q < staged * 3; q += 32) {
+        const unsigned long long rec = base + q / 3;
+        if (rec < p.cap) scratch[rec * 3 + q % 3] = sink.stage[q];
+    }
+    if (nvalid > (uint32_t)kStagePerWarp) {
+        // rare (degenerate input such as a constant buffer): second pass over the range
+        sink.scratch = scratch;
+        sink.dst0 = base;
+        sink.seq = 0;
+        sink.gate = 0;
+        scan_warp_range<FMT>(lv, wcands, lane, sink);
     }
 }
 
@@ -592,10 +579,11 @@ __global__ void levels_cs16_kernel(const uint32_t *iq, unsigned long long n, uin
 cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream)
 {
     if (p.n_tiles == 0) return cudaSuccess;
+    const unsigned grid = (p.n_tiles + kWarps - 1) / kWarps;
     if (format == AIRGPU_FMT_U8)
-        decode_kernel<AIRGPU_FMT_U8><<<p.n_tiles, kThreads, 0, stream>>>(p);
+        decode_kernel<AIRGPU_FMT_U8><<<grid, kThreads, 0, stream>>>(p);
     else
-        decode_kernel<AIRGPU_FMT_CS16><<<p.n_tiles, kThreads, 0, stream>>>(p);
+        decode_kernel<AIRGPU_FMT_CS16><<<grid, kThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

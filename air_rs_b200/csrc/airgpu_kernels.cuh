@@ -20,9 +20,9 @@ constexpr int kWarpTile = 2048;                   // candidate offsets per warp
 constexpr int kHalo = 256;                        // a candidate at i reads samples [i, i+240): 239 needed, 256 keeps 16-byte chunks
 constexpr int kWarpLevels = kWarpTile + kHalo;    // u16 levels staged per warp
 constexpr int kWarpChunks = kWarpLevels / 8;      // 16-byte chunks (8 levels each): 288 = 9 per lane
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;                     // 4 independent warps per CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kTile = kWarps * kWarpTile;         // candidate offsets per CTA (one tile_tab entry)
+constexpr int kTile = kWarpTile;                  // ordering unit: one tile_tab entry per warp tile
 constexpr int kStagePerWarp = 16;                 // frames a warp stages before falling back to a second pass
 constexpr int kFrameSamples = 240;                // 16 + 112 * 2, reference src/adsb.rs:98
 constexpr int kGroupTiles = 256;                  // tiles per ordering group (one gather CTA)
