@@ -88,7 +88,7 @@ struct airgpu_ctx {
     airgpu_frame *scratch = nullptr;
     size_t scratch_cap = 0;
     uint2 *tile_tab = nullptr;
-    unsigned long long *group_sum = nullptr;   // 2 * groups_cap: sums, then bases
+    unsigned long long *group_sum = nullptr;   // 3 * groups_cap: frame sums, gate sums, bases
     size_t groups_cap = 0;
     size_t tiles_cap = 0;
     unsigned long long *counters = nullptr;   // kNumCounters + 1 (last = running frame total)
@@ -121,7 +121,7 @@ int ensure_tiles(airgpu_ctx *c, size_t n_tiles)
     size_t want = std::max<size_t>(n_tiles, 1024);
     size_t groups = (want + kGroupTiles - 1) / kGroupTiles;
     CU(cudaMalloc(&c->tile_tab, want * sizeof(uint2)));
-    CU(cudaMalloc(&c->group_sum, 2 * groups * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->group_sum, 3 * groups * sizeof(unsigned long long)));
     c->tiles_cap = want;
     c->groups_cap = groups;
     return AIRGPU_OK;
@@ -162,12 +162,14 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     if (!make_geometry(n, seg, g)) return fail(AIRGPU_ERR_INVALID, "capture too large for one call (%zu samples)", n);
     int rc;
     if ((rc = ensure_tiles(c, g.n_tiles)) != AIRGPU_OK) return rc;
-    if ((rc = ensure_scratch(c, std::max<size_t>(cap, 1))) != AIRGPU_OK) return rc;
+    // scratch = kSlotsPerTile fixed record slots per tile + an overflow area as large as the output
+    const size_t ovf_cap = std::max<size_t>(cap, 1);
+    if ((rc = ensure_scratch(c, (size_t)g.n_tiles * kSlotsPerTile + ovf_cap)) != AIRGPU_OK) return rc;
 
-    // the scratch index and the per-group sums restart with every piece
-    CU(cudaMemsetAsync(c->counters + kCounterFrames, 0, sizeof(unsigned long long), stream));
+    // the overflow index and the per-group sums restart with every piece
+    CU(cudaMemsetAsync(c->counters + kCounterOverflow, 0, sizeof(unsigned long long), stream));
     const size_t n_groups = (g.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    if (n_groups) CU(cudaMemsetAsync(c->group_sum, 0, n_groups * sizeof(unsigned long long), stream));
+    if (n_groups) CU(cudaMemsetAsync(c->group_sum, 0, 2 * c->groups_cap * sizeof(unsigned long long), stream));
 
     DecodeParams p{};
     p.iq = d_iq;
@@ -179,10 +181,12 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.vec_ok = ((reinterpret_cast<uintptr_t>(d_iq) & 15u) == 0 && (g.n_tiles == g.tiles_per_seg || g.seg_len % 8 == 0)) ? 1u : 0u;
     p.scratch = c->scratch;
     p.cap = cap;
+    p.ovf_cap = ovf_cap;
     p.counters = c->counters;
     p.tile_tab = c->tile_tab;
     p.group_sum = c->group_sum;
-    p.group_base = c->group_sum + c->groups_cap;
+    p.group_gate = c->group_sum + c->groups_cap;
+    p.group_base = c->group_sum + 2 * c->groups_cap;
     CU(cudaEventRecord(c->evk0, stream));
     CU(launch_decode(c->format, p, stream));
     CU(cudaEventRecord(c->evk1, stream));

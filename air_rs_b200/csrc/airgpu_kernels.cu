@@ -251,14 +251,15 @@ __device__ __forceinline__ uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c) {
 template <int FMT>
 __device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
 
-// Where the frames a warp finds go: pass 0 stages the first kStagePerWarp in shared
-// memory (the output position is not known yet); pass 1, only run when a warp found
-// more than that, writes the rest straight to their final scratch slots.
+// Where the frames a warp finds go.  Every tile owns kSlotsPerTile fixed record slots in
+// scratch (slot index = tile * kSlotsPerTile), so the common case needs no reservation, no
+// atomic with a return value and no staging: records are written as they are found, in
+// offset order.  A tile with more frames than slots (degenerate input such as a constant
+// buffer) reserves an overflow range once and a second pass writes the rest there.
 struct Sink {
-    unsigned long long *stage;      // [kStagePerWarp][3]
-    unsigned long long *scratch;    // global records, nullptr in pass 0
-    unsigned long long dst0;        // first scratch record of this warp
-    unsigned long long cap;
+    unsigned long long *slots;      // this tile's fixed slots in scratch (u64 view)
+    unsigned long long *overflow;   // overflow range (u64 view), nullptr in pass 0
+    unsigned long long ovf_room;    // records that fit the overflow range
     unsigned long long off0;        // frame offset of the warp's candidate 0
     uint32_t seq;                   // valid frames seen so far in this pass
     uint32_t gate;                  // gate passes (reference num_processed)
@@ -338,13 +339,13 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
                 sink.gate += 1;
                 const Cand c = process_candidate(lv, i, lane);
                 if (c.valid) {
-                    if (sink.scratch == nullptr) {
-                        if (sink.seq < (uint32_t)kStagePerWarp && lane < 3)
-                            sink.stage[sink.seq * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
-                    } else if (sink.seq >= (uint32_t)kStagePerWarp) {
-                        const unsigned long long rec = sink.dst0 + sink.seq;
-                        if (lane < 3 && rec < sink.cap)
-                            sink.scratch[rec * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
+                    if (sink.overflow == nullptr) {
+                        if (sink.seq < (uint32_t)kSlotsPerTile && lane < 3)
+                            sink.slots[sink.seq * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
+                    } else if (sink.seq >= (uint32_t)kSlotsPerTile) {
+                        const unsigned long long r = sink.seq - kSlotsPerTile;
+                        if (lane < 3 && r < sink.ovf_room)
+                            sink.overflow[r * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
                     }
                     sink.seq += 1;
                 }
@@ -360,7 +361,6 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
     // private slice of shared memory, its own stage and its own output reservation.  The CTA
     // is only a packaging unit (4 warps keep the per-CTA footprint small: 8 CTAs per SM).
     __shared__ __align__(128) uint16_t s_lvl[kWarps][kWarpLevelsPadded];
-    __shared__ unsigned long long s_stage[kWarps][kStagePerWarp * 3];
 
     constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
     constexpr int kChunkBytes = 8 * BPS;
@@ -389,11 +389,11 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
         return;
     }
     uint16_t *lv = s_lvl[warp];
+    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
     Sink sink;
-    sink.stage = s_stage[warp];
-    sink.scratch = nullptr;
-    sink.dst0 = 0;
-    sink.cap = p.cap;
+    sink.slots = scratch + (unsigned long long)tile * (kSlotsPerTile * 3);
+    sink.overflow = nullptr;
+    sink.ovf_room = 0;
     sink.off0 = p.base_offset + seg_start + wpos;
     sink.seq = 0;
     sink.gate = 0;
@@ -447,33 +447,25 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
     }
     __syncwarp();
 
-    // ---- phase 2+3: gate, slice, CRC; first kStagePerWarp frames staged ----
+    // ---- phase 2+3: gate, slice, CRC; frames go straight to the tile's scratch slots ----
     scan_warp_range<FMT>(lv, wcands, lane, sink);
     const uint32_t nvalid = sink.seq;
 
-    // ---- phase 4: this warp reserves its own output space and writes its records ----
-    unsigned long long base = 0;
+    // ---- phase 4: publish the count (no atomic with a return value on the common path) ----
+    unsigned long long ovf_base = 0;
     if (lane == 0) {
-        if (nvalid) {
-            base = atomicAdd(&p.counters[kCounterFrames], (unsigned long long)nvalid);
-            atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)nvalid);
-        }
-        if (sink.gate) atomicAdd(&p.counters[kCounterGate], (unsigned long long)sink.gate);
-        p.tile_tab[tile] = make_uint2((unsigned)min(base, 0xFFFFFFFFull), nvalid);
+        if (nvalid) atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)nvalid);            // RED
+        if (sink.gate) atomicAdd(&p.group_gate[tile / kGroupTiles], (unsigned long long)sink.gate);    // RED
+        if (nvalid > (uint32_t)kSlotsPerTile)
+            ovf_base = atomicAdd(&p.counters[kCounterOverflow], (unsigned long long)(nvalid - kSlotsPerTile));
+        p.tile_tab[tile] = make_uint2((unsigned)min(ovf_base, 0xFFFFFFFFull), nvalid);
     }
-    if (nvalid == 0) return;
-    base = __shfl_sync(kFull, base, 0);
-    __syncwarp();                                    // stage writes (lanes 0..2) visible to the warp
-    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
-    const uint32_t staged = min(nvalid, (uint32_t)kStagePerWarp);
-    for (uint32_t q = lane; q < staged * 3; q += 32) {
-        const unsigned long long rec = base + q / 3;
-        if (rec < p.cap) scratch[rec * 3 + q % 3] = sink.stage[q];
-    }
-    if (nvalid > (uint32_t)kStagePerWarp) {
-        // rare (degenerate input such as a constant buffer): second pass over the range
-        sink.scratch = scratch;
-        sink.dst0 = base;
+    if (nvalid > (uint32_t)kSlotsPerTile) {
+        // rare (degenerate input): second pass over the range writes frames kSlotsPerTile.. to
+        // the overflow area, which starts after all the fixed slots
+        ovf_base = __shfl_sync(kFull, ovf_base, 0);
+        sink.overflow = scratch + ((unsigned long long)p.n_tiles * kSlotsPerTile + ovf_base) * 3;
+        sink.ovf_room = p.ovf_cap > ovf_base ? p.ovf_cap - ovf_base : 0ull;
         sink.seq = 0;
         sink.gate = 0;
         scan_warp_range<FMT>(lv, wcands, lane, sink);
@@ -518,11 +510,12 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 }
 
 __global__ void __launch_bounds__(kScanThreads, 1)
-group_scan_kernel(const unsigned long long *group_sum, unsigned n_groups, unsigned long long *group_base,
-                  unsigned long long *d_total)
+group_scan_kernel(const unsigned long long *group_sum, const unsigned long long *group_gate, unsigned n_groups,
+                  unsigned long long *group_base, unsigned long long *d_total, unsigned long long *d_gate)
 {
     __shared__ unsigned long long s_warp[33];
     unsigned long long running = *d_total;   // frames already in `out` (pieces of one call append)
+    unsigned long long gate = 0;
     for (unsigned base = 0; base < n_groups; base += kScanThreads) {
         const unsigned g = base + threadIdx.x;
         const unsigned long long v = g < n_groups ? group_sum[g] : 0ull;
@@ -530,13 +523,19 @@ group_scan_kernel(const unsigned long long *group_sum, unsigned n_groups, unsign
         const unsigned long long excl = block_exclusive_scan(v, s_warp, &total);
         if (g < n_groups) group_base[g] = running + excl;
         running += total;
+        unsigned long long gsum;
+        (void)block_exclusive_scan(g < n_groups ? group_gate[g] : 0ull, s_warp, &gsum);
+        gate += gsum;
     }
-    if (threadIdx.x == 0) *d_total = running;
+    if (threadIdx.x == 0) {
+        *d_total = running;
+        *d_gate += gate;                     // gate passes accumulate over the pieces of a call
+    }
 }
 
 __global__ void __launch_bounds__(kGroupTiles)
 gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const unsigned long long *group_base,
-              unsigned n_tiles, unsigned long long *out, unsigned long long cap)
+              unsigned n_tiles, unsigned long long *out, unsigned long long cap, unsigned long long ovf_cap)
 {
     __shared__ unsigned long long s_warp[33];
     __shared__ unsigned long long s_pos[kGroupTiles];
@@ -555,9 +554,16 @@ gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const un
         const uint2 ek = s_tab[k];
         if (ek.y == 0) continue;
         const unsigned long long pos = s_pos[k];
+        const unsigned long long slot0 = (unsigned long long)(t0 + k) * kSlotsPerTile;
+        const unsigned long long ovf0 = (unsigned long long)n_tiles * kSlotsPerTile + ek.x;
         for (unsigned q = lane; q < ek.y * 3; q += 32) {
-            const unsigned long long src = (unsigned long long)ek.x + q / 3, dst = pos + q / 3;
-            if (src < cap && dst < cap) out[dst * 3 + q % 3] = scratch[src * 3 + q % 3];
+            const unsigned r = q / 3;
+            const unsigned long long dst = pos + r;
+            if (dst >= cap) continue;
+            if (r < (unsigned)kSlotsPerTile)
+                out[dst * 3 + q % 3] = scratch[(slot0 + r) * 3 + q % 3];
+            else if ((unsigned long long)ek.x + (r - kSlotsPerTile) < ovf_cap)
+                out[dst * 3 + q % 3] = scratch[(ovf0 + (r - kSlotsPerTile)) * 3 + q % 3];
         }
     }
 }
@@ -591,13 +597,14 @@ cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned l
                             cudaStream_t stream)
 {
     const unsigned n_groups = (p.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    group_scan_kernel<<<1, kScanThreads, 0, stream>>>(p.group_sum, n_groups, p.group_base, d_total);
+    group_scan_kernel<<<1, kScanThreads, 0, stream>>>(p.group_sum, p.group_gate, n_groups, p.group_base, d_total,
+                                                       p.counters + kCounterGate);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (n_groups == 0) return cudaSuccess;
     gather_kernel<<<n_groups, kGroupTiles, 0, stream>>>(reinterpret_cast<const unsigned long long *>(p.scratch),
                                                         p.tile_tab, p.group_base, p.n_tiles,
-                                                        reinterpret_cast<unsigned long long *>(out), p.cap);
+                                                        reinterpret_cast<unsigned long long *>(out), p.cap, p.ovf_cap);
     return cudaGetLastError();
 }
 

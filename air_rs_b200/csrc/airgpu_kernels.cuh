@@ -23,7 +23,7 @@ constexpr int kWarpChunks = kWarpLevels / 8;      // 16-byte chunks (8 levels ea
 constexpr int kThreads = 128;                     // 4 independent warps per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = kWarpTile;                  // ordering unit: one tile_tab entry per warp tile
-constexpr int kStagePerWarp = 16;                 // frames a warp stages before falling back to a second pass
+constexpr int kSlotsPerTile = 16;                 // fixed scratch record slots per tile; more frames than that go to the overflow area
 constexpr int kFrameSamples = 240;                // 16 + 112 * 2, reference src/adsb.rs:98
 constexpr int kGroupTiles = 256;                  // tiles per ordering group (one gather CTA)
 
@@ -35,15 +35,17 @@ struct DecodeParams {
     unsigned int n_tiles;           // n_segments * tiles_per_seg
     unsigned int vec_ok;            // every warp slice starts 16-byte aligned (base aligned, seg_len % 8 == 0)
     unsigned long long base_offset; // added to every frame offset
-    airgpu_frame *scratch;          // unordered-between-tiles frame records
-    unsigned long long cap;         // capacity of scratch (and of the final output)
-    unsigned long long *counters;   // [0] frames, [1] gate passes, [2] preamble passes
-    uint2 *tile_tab;                // per tile: (base index into scratch, frame count)
+    airgpu_frame *scratch;          // n_tiles * kSlotsPerTile fixed slots, then ovf_cap overflow records
+    unsigned long long cap;         // capacity of the final output
+    unsigned long long ovf_cap;     // capacity of the overflow area
+    unsigned long long *counters;   // see the enum below
+    uint2 *tile_tab;                // per tile: (overflow base, frame count)
     unsigned long long *group_sum;  // per group of kGroupTiles tiles: frames (zeroed before the launch)
+    unsigned long long *group_gate; // per group: gate passes (zeroed before the launch)
     unsigned long long *group_base; // per group: ordered position of its first frame
 };
 
-enum { kCounterFrames = 0, kCounterGate = 1, kCounterPreamble = 2, kNumCounters = 4 };
+enum { kCounterOverflow = 0, kCounterGate = 1, kNumCounters = 4 };
 
 // Launchers (stream-ordered, no synchronisation inside).
 cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream);
