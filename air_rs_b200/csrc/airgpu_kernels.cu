@@ -265,15 +265,40 @@ struct Sink {
     uint32_t gate;                  // gate passes (reference num_processed)
 };
 
+// One survivor of the gate: slice, CRC, repair, emit (warp-cooperative, warp-uniform i).
+__device__ __forceinline__ void emit_candidate(const uint16_t *lv, int i, int lane, Sink &sink)
+{
+    sink.gate += 1;
+    const Cand c = process_candidate(lv, i, lane);
+    if (!c.valid) return;
+    if (sink.overflow == nullptr) {
+        if (sink.seq < (uint32_t)kSlotsPerTile && lane < 3)
+            sink.slots[sink.seq * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
+    } else if (sink.seq >= (uint32_t)kSlotsPerTile) {
+        const unsigned long long r = sink.seq - kSlotsPerTile;
+        if (lane < 3 && r < sink.ovf_room)
+            sink.overflow[r * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
+    }
+    sink.seq += 1;
+}
+
 // Gate + slice + CRC over the warp's candidates [0, wcands): the reference's offset
 // loop (adsb.rs:98-114) for this range, emitting in ascending offset order.
+//
+// The preamble test runs over the whole tile first (four 512-offset iterations, no
+// divergence); each lane only records WHICH of its offsets passed, as bits.  The DF test and
+// the survivors are then handled once per tile, so the cost of leaving the fast path is
+// paid once per 2048 offsets instead of once per 512 (in dense traffic nearly every
+// 512-offset block contains a real preamble).
 template <int FMT>
 __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, int lane, Sink &sink)
 {
+    // hit bits: iteration `it` lives in pm[it >> 1] at bit 8*j + 4*(it & 1) + q  <->  offset
+    // it*512 + lane*16 + 4*q + j   (q = 0..3: which F register, j = 0..3: which byte of it)
+    uint32_t pmA = 0u, pmB = 0u;   // iterations 0-1, 2-3
 #pragma unroll 1
     for (int it = 0; it * 512 < wcands; ++it) {
         // lane owns offsets [ob, ob+16); E[t] = (level[ob+2t], level[ob+2t+1])
-        const int ob = it * 512 + lane * 16;
         const int cb = it * 64 + lane * 2;
         uint32_t E[16];
 #pragma unroll
@@ -297,8 +322,8 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
         //   highs 0,2,7,9               -> E[t], E[t+1], O[t+3], O[t+4]
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
         // F[q] gathers the fail flags of four consecutive offsets (ob+4q .. ob+4q+3) into the
-        // top bits of its four bytes, so the rare path below gets positions almost for free.
-        uint32_t F[4];
+        // top bits of its four bytes.
+        uint32_t hits = 0u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t d[2];
@@ -309,46 +334,46 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
                 const uint32_t lo = min3u2<FMT>(min3u2<FMT>(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
                 d[h] = fail_bits<FMT>(lo, hi);
             }
-            F[q] = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
+            const uint32_t F = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
+            hits |= (~F >> (7 - q)) & (0x01010101u << q);
         }
-        const uint32_t allfail = F[0] & F[1] & F[2] & F[3] & 0x80808080u;
-        if (!__any_sync(kFull, allfail != 0x80808080u)) continue;
+        hits <<= 4 * (it & 1);
+        if (it < 2) pmA |= hits;
+        else pmB |= hits;
+    }
+    if (!__any_sync(kFull, (pmA | pmB) != 0u)) return;
 
-        // ---- some lane saw a preamble: DF test per hit, then the survivors ----
-        uint32_t cm = 0u;   // bit o: offset ob + o passes the whole gate
-        if (allfail != 0x80808080u) {
-            uint32_t pm = 0u;   // bit 8*j + q: offset ob + 4q + j passed the preamble test
+    // ---- DF test for every preamble hit of this lane (all iterations at once) ----
+    uint32_t cmA = 0u, cmB = 0u;   // bit 16*(it & 1) + o: offset it*512 + lane*16 + o passes the gate (A: it 0-1, B: it 2-3)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pm |= (~F[q] >> (7 - q)) & (0x01010101u << q);
-            while (pm) {
-                const int b = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const int o = 4 * (b & 7) + (b >> 3);
-                if (ob + o < wcands && df17_ok(lv, ob + o)) cm |= 1u << o;
-            }
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? pmB : pmA;
+        uint32_t c = 0u;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int it = 2 * half + ((b >> 2) & 1);
+            const int o = 4 * (b & 3) + (b >> 3);
+            const int i = it * 512 + lane * 16 + o;
+            if (i < wcands && df17_ok(lv, i)) c |= 1u << (16 * (it & 1) + o);
         }
-        unsigned lanes = __ballot_sync(kFull, cm != 0u);
+        if (half) cmB = c;
+        else cmA = c;
+    }
+
+    // ---- survivors, in ascending offset order: iteration, then lane, then bit ----
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const uint32_t mine = ((it < 2 ? cmA : cmB) >> (16 * (it & 1))) & 0xFFFFu;
+        unsigned lanes = __ballot_sync(kFull, mine != 0u);
         while (lanes) {
             const int src_lane = __ffs(lanes) - 1;
             lanes &= lanes - 1;
-            uint32_t bits = __shfl_sync(kFull, cm, src_lane);
+            uint32_t bits = __shfl_sync(kFull, mine, src_lane);
             while (bits) {
                 const int o = __ffs(bits) - 1;
                 bits &= bits - 1;
-                const int i = it * 512 + src_lane * 16 + o;
-                sink.gate += 1;
-                const Cand c = process_candidate(lv, i, lane);
-                if (c.valid) {
-                    if (sink.overflow == nullptr) {
-                        if (sink.seq < (uint32_t)kSlotsPerTile && lane < 3)
-                            sink.slots[sink.seq * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
-                    } else if (sink.seq >= (uint32_t)kSlotsPerTile) {
-                        const unsigned long long r = sink.seq - kSlotsPerTile;
-                        if (lane < 3 && r < sink.ovf_room)
-                            sink.overflow[r * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
-                    }
-                    sink.seq += 1;
-                }
+                emit_candidate(lv, it * 512 + src_lane * 16 + o, lane, sink);
             }
         }
     }
