@@ -189,14 +189,19 @@ __device__ __forceinline__ Cand process_candidate(const uint16_t *s, int i, int 
     uint32_t part = 0;
     uint32_t w[4];
     uint32_t syn_of[4];
+    // lane handles bits k = lane + 32 r: levels j and j+1 with j = i + 16 + 2 k.  Consecutive
+    // rounds are 64 levels = 72 padded positions apart, so the two padded indices are computed
+    // once (the pair may straddle a pad, hence two of them).
+    const int j = i + 16 + 2 * lane;
+    const uint16_t *p0 = s + phys_idx(j);
+    const uint16_t *p1 = s + phys_idx(j + 1);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int k = 32 * r + lane;
         const bool act = (r < 3) || (lane < 16);              // k < 112
-        const int j = i + 16 + 2 * k;
         bool bit = false;
         syn_of[r] = act ? __ldg(&g_syn.v[k]) : 0u;
-        if (act) bit = lvl(s, j) < lvl(s, j + 1);              // m[2k] > m[2k+1]  (demod.rs:104)
+        if (act) bit = p0[72 * r] < p1[72 * r];                // m[2k] > m[2k+1]  (demod.rs:104)
         w[r] = __brev(__ballot_sync(kFull, bit));
         if (bit) part ^= syn_of[r];
     }
@@ -296,14 +301,18 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
     // hit bits: iteration `it` lives in pm[it >> 1] at bit 8*j + 4*(it & 1) + q  <->  offset
     // it*512 + lane*16 + 4*q + j   (q = 0..3: which F register, j = 0..3: which byte of it)
     uint32_t pmA = 0u, pmB = 0u;   // iterations 0-1, 2-3
+    // window chunks 2*lane + q of iteration `it` sit at padded chunk pc[q] + 72*it
+    const uint4 *lv4 = reinterpret_cast<const uint4 *>(lv);
+    int pc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pc[q] = phys_chunk(2 * lane + q);
 #pragma unroll 1
     for (int it = 0; it * 512 < wcands; ++it) {
         // lane owns offsets [ob, ob+16); E[t] = (level[ob+2t], level[ob+2t+1])
-        const int cb = it * 64 + lane * 2;
         uint32_t E[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(&lv[phys_chunk(cb + q) << 3]);
+            const uint4 v = lv4[pc[q] + 72 * it];
             E[4 * q + 0] = v.x;
             E[4 * q + 1] = v.y;
             E[4 * q + 2] = v.z;
@@ -428,12 +437,15 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
     if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
         // 9 chunks per lane in three batches; the loads of batch g+1 are in flight while
         // batch g is converted, so a warp waits for HBM once per tile, not three times
+        // chunk c = lane + 32 m is stored at padded chunk (lane + lane/8) + 36 m: both the global
+        // and the shared address are "per-lane base + compile-time offset"
+        const uint8_t *gsrc = src + lane * kChunkBytes;
+        uint4 *sdst = reinterpret_cast<uint4 *>(lv) + (lane + (lane >> 3));
         uint4 a[3], b[3], na[3], nb[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const int c = lane + 32 * j;
-            a[j] = ldg_stream(src + c * kChunkBytes);
-            if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(src + c * kChunkBytes + 16);
+            a[j] = ldg_stream(gsrc + 32 * j * kChunkBytes);
+            if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(gsrc + 32 * j * kChunkBytes + 16);
         }
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
