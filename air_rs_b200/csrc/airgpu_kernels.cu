@@ -306,8 +306,10 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
     int pc[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) pc[q] = phys_chunk(2 * lane + q);
-#pragma unroll 1
-    for (int it = 0; it * 512 < wcands; ++it) {
+    // fully unrolled: shared-memory offsets and hit-bit positions become immediates
+#pragma unroll
+    for (int it = 0; it < kWarpTile / 512; ++it) {
+        if (it * 512 >= wcands) break;
         // lane owns offsets [ob, ob+16); E[t] = (level[ob+2t], level[ob+2t+1])
         uint32_t E[16];
 #pragma unroll
@@ -332,7 +334,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
         // F[q] gathers the fail flags of four consecutive offsets (ob+4q .. ob+4q+3) into the
         // top bits of its four bytes.
-        uint32_t hits = 0u;
+        uint32_t fails = 0u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t d[2];
@@ -344,9 +346,9 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
                 d[h] = fail_bits<FMT>(lo, hi);
             }
             const uint32_t F = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
-            hits |= (~F >> (7 - q)) & (0x01010101u << q);
+            fails |= (F >> (7 - q)) & (0x01010101u << q);
         }
-        hits <<= 4 * (it & 1);
+        const uint32_t hits = (~fails & 0x0F0F0F0Fu) << (4 * (it & 1));
         if (it < 2) pmA |= hits;
         else pmB |= hits;
     }
