@@ -72,12 +72,13 @@ __device__ __forceinline__ int phys_idx(int i) { return i + ((i >> 6) << 3); }
 
 // ---- per-sample level -------------------------------------------------------
 // U8: one 32-bit word = (I0, Q0, I1, Q1).  Returns (level0 | level1 << 16).
-__device__ __forceinline__ uint32_t levels_u8_pair(uint32_t w)
+__device__ __forceinline__ uint32_t levels_u8_pair(uint32_t w, uint32_t minus_one)
 {
     // z = I*(255-I) + Q*(255-Q) <= 32512 per sample.  The integer ALU pipe is the busy
     // one in this kernel, so the complement is taken as w * -1 + -1 (IMAD, FMA pipe):
-    uint32_t nw;
-    asm("mad.lo.u32 %0, %1, 0xFFFFFFFF, 0xFFFFFFFF;" : "=r"(nw) : "r"(w));   // ~w
+    // with `minus_one` = 0xFFFFFFFF passed as a kernel parameter so that ptxas cannot turn
+    // it back into an integer-pipe negate
+    const uint32_t nw = w * minus_one + minus_one;            // ~w
     const uint32_t zsum = __dp4a(nw, w, 0u);                  // z0 + z1
     const uint32_t z1 = __dp4a(nw, w & 0xFFFF0000u, 0u);      // z1
     return zsum + z1 * 65535u;                                // z0 + (z1 << 16)
@@ -99,14 +100,14 @@ __device__ __forceinline__ uint32_t level_cs16(uint32_t w)
 }
 
 template <int FMT>
-__device__ __forceinline__ uint4 levels_of_chunk(uint4 a, uint4 b)
+__device__ __forceinline__ uint4 levels_of_chunk(uint4 a, uint4 b, uint32_t minus_one)
 {
     uint4 o;
     if (FMT == AIRGPU_FMT_U8) {           // a = 8 samples, b unused
-        o.x = levels_u8_pair(a.x);
-        o.y = levels_u8_pair(a.y);
-        o.z = levels_u8_pair(a.z);
-        o.w = levels_u8_pair(a.w);
+        o.x = levels_u8_pair(a.x, minus_one);
+        o.y = levels_u8_pair(a.y, minus_one);
+        o.z = levels_u8_pair(a.z, minus_one);
+        o.w = levels_u8_pair(a.w, minus_one);
     } else {                              // a, b = 4 samples each
         o.x = level_cs16(a.x) | (level_cs16(a.y) << 16);
         o.y = level_cs16(a.z) | (level_cs16(a.w) << 16);
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int c = lane + 32 * (3 * g + j);
-                *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j]);
+                *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j], p.minus_one);
             }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
                 a = load16_guarded(src, (long long)c * kChunkBytes, avail);
                 if (FMT == AIRGPU_FMT_CS16) b = load16_guarded(src, (long long)c * kChunkBytes + 16, avail);
             }
-            *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b);
+            *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b, p.minus_one);
         }
     }
     __syncwarp();
@@ -607,10 +608,10 @@ gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const un
     }
 }
 
-__global__ void levels_u8_kernel(uint16_t *out)
+__global__ void levels_u8_kernel(uint16_t *out, uint32_t minus_one)
 {
     unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = I | Q << 8
-    if (idx < 65536u) out[idx] = (uint16_t)(levels_u8_pair(idx) & 0xFFFFu);
+    if (idx < 65536u) out[idx] = (uint16_t)(levels_u8_pair(idx, minus_one) & 0xFFFFu);
 }
 
 __global__ void levels_cs16_kernel(const uint32_t *iq, unsigned long long n, uint16_t *out)
@@ -649,7 +650,7 @@ cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned l
 
 cudaError_t launch_levels_u8(uint16_t *out65536, cudaStream_t stream)
 {
-    levels_u8_kernel<<<256, 256, 0, stream>>>(out65536);
+    levels_u8_kernel<<<256, 256, 0, stream>>>(out65536, 0xFFFFFFFFu);
     return cudaGetLastError();
 }
 
