@@ -297,7 +297,7 @@ __device__ __forceinline__ void emit_candidate(const uint16_t *lv, int i, int la
 // paid once per 2048 offsets instead of once per 512 (in dense traffic nearly every
 // 512-offset block contains a real preamble).
 template <int FMT>
-__device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, int lane, Sink &sink)
+__device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hitlist, int wcands, int lane, Sink &sink)
 {
     // hit bits: iteration `it` lives in pm[it >> 1] at bit 8*j + 4*(it & 1) + q  <->  offset
     // it*512 + lane*16 + 4*q + j   (q = 0..3: which F register, j = 0..3: which byte of it)
@@ -353,11 +353,51 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
         if (it < 2) pmA |= hits;
         else pmB |= hits;
     }
-    if (!__any_sync(kFull, (pmA | pmB) != 0u)) return;
+    // ---- preamble hits of the whole tile ----
+    const uint32_t nh = __popc(pmA) + __popc(pmB);
+    const uint32_t total_hits = __reduce_add_sync(kFull, nh);
+    if (total_hits == 0u) return;
 
-    // ---- DF test for every preamble hit of this lane (all iterations at once) ----
-    uint32_t cmA = 0u, cmB = 0u;   // bit 16*(it & 1) + o: offset it*512 + lane*16 + o passes the gate (A: it 0-1, B: it 2-3)
+    if (total_hits <= 32u) {
+        // Usual case (a handful of hits per 2048 offsets): spread them over the lanes, one
+        // hit per lane, so the DF test runs once for all of them instead of once per hit of
+        // the busiest lane; survivors are then emitted in ascending offset order by repeated
+        // warp-wide minimum.
+        uint32_t incl = nh;
 #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += y;
+        }
+        uint32_t pos = incl - nh;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t m = half ? pmB : pmA;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int it = 2 * half + ((b >> 2) & 1);
+                hitlist[pos++] = (uint16_t)(it * 512 + lane * 16 + 4 * (b & 3) + (b >> 3));
+            }
+        }
+        __syncwarp();
+        uint32_t key = 0xFFFFFFFFu;
+        if ((uint32_t)lane < total_hits) {
+            const int i = hitlist[lane];
+            if (i < wcands && df17_ok(lv, i)) key = (uint32_t)i;
+        }
+        for (;;) {
+            const uint32_t next = __reduce_min_sync(kFull, key);
+            if (next == 0xFFFFFFFFu) break;
+            emit_candidate(lv, (int)next, lane, sink);
+            if (key == next) key = 0xFFFFFFFFu;
+        }
+        return;
+    }
+
+    // ---- many hits (degenerate input, e.g. a constant buffer): per-lane DF loops ----
+    uint32_t cmA = 0u, cmB = 0u;   // bit 16*(it & 1) + o: offset it*512 + lane*16 + o passes the gate (A: it 0-1, B: it 2-3)
+#pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         uint32_t m = half ? pmB : pmA;
         uint32_t c = 0u;
@@ -372,8 +412,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, int wcands, 
         if (half) cmB = c;
         else cmA = c;
     }
-
-    // ---- survivors, in ascending offset order: iteration, then lane, then bit ----
+    // survivors, in ascending offset order: iteration, then lane, then bit
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {
         const uint32_t mine = ((it < 2 ? cmA : cmB) >> (16 * (it & 1))) & 0xFFFFu;
@@ -398,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
     // private slice of shared memory, its own stage and its own output reservation.  The CTA
     // is only a packaging unit (4 warps keep the per-CTA footprint small: 8 CTAs per SM).
     __shared__ __align__(128) uint16_t s_lvl[kWarps][kWarpLevelsPadded];
+    __shared__ uint16_t s_hits[kWarps][32];
 
     constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
     constexpr int kChunkBytes = 8 * BPS;
@@ -488,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
     __syncwarp();
 
     // ---- phase 2+3: gate, slice, CRC; frames go straight to the tile's scratch slots ----
-    scan_warp_range<FMT>(lv, wcands, lane, sink);
+    scan_warp_range<FMT>(lv, s_hits[warp], wcands, lane, sink);
     const uint32_t nvalid = sink.seq;
 
     // ---- phase 4: publish the count (no atomic with a return value on the common path) ----
@@ -508,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
         sink.ovf_room = p.ovf_cap > ovf_base ? p.ovf_cap - ovf_base : 0ull;
         sink.seq = 0;
         sink.gate = 0;
-        scan_warp_range<FMT>(lv, wcands, lane, sink);
+        scan_warp_range<FMT>(lv, s_hits[warp], wcands, lane, sink);
     }
 }
 
