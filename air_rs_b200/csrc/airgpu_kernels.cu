@@ -158,19 +158,17 @@ __device__ __forceinline__ uint32_t fail_bits(uint32_t lo, uint32_t hi)
 __device__ __forceinline__ uint32_t lvl(const uint16_t *s, int i) { return s[phys_idx(i)]; }
 
 // DF = 17 test on the first five data bits (demod.rs:45-54), inverted levels.
+// Levels j..j+9 are consecutive in shared memory except that one pad (8 positions) may fall
+// inside the run: two base pointers and a per-level select keep it branch free.
 __device__ __forceinline__ bool df17_ok(const uint16_t *s, int i)
 {
     const int j = i + 16;
-    const uint16_t *q = s + phys_idx(j);
+    const uint16_t *qa = s + phys_idx(j);
+    const uint16_t *qb = qa + 8;
+    const int cross = 64 - (j & 63);      // first k that lies behind the pad (>= 10: none)
     uint32_t v[10];
-    if ((j & 63) <= 54) {                 // levels j..j+9 lie between two pads
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = q[k];
-    } else {
-        const int cross = 64 - (j & 63);
-#pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = q[k + (k >= cross ? 8 : 0)];
-    }
+    for (int k = 0; k < 10; ++k) v[k] = (k >= cross ? qb : qa)[k];
     const uint32_t hi = max(max(max(v[0], v[3]), max(v[5], v[7])), v[8]);
     const uint32_t lo = min(min(min(v[1], v[2]), min(v[4], v[6])), v[9]);
     return hi <= lo;
@@ -299,8 +297,9 @@ __device__ __forceinline__ void emit_candidate(const uint16_t *lv, int i, int la
 template <int FMT>
 __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hitlist, int wcands, int lane, Sink &sink)
 {
-    // hit bits: iteration `it` lives in pm[it >> 1] at bit 8*j + 4*(it & 1) + q  <->  offset
-    // it*512 + lane*16 + 4*q + j   (q = 0..3: which F register, j = 0..3: which byte of it)
+    // hit bits: iteration `it` lives in pmA (it 0-1) / pmB (it 2-3) at bit
+    // 8*j + 7 - 4*(it & 1) - q  <->  offset it*512 + lane*16 + 4*q + j
+    // (q = 0..3: which F register, j = 0..3: which byte of it)
     uint32_t pmA = 0u, pmB = 0u;   // iterations 0-1, 2-3
     // window chunks 2*lane + q of iteration `it` sit at padded chunk pc[q] + 72*it
     const uint4 *lv4 = reinterpret_cast<const uint4 *>(lv);
@@ -335,7 +334,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
         // F[q] gathers the fail flags of four consecutive offsets (ob+4q .. ob+4q+3) into the
         // top bits of its four bytes.
-        uint32_t fails = 0u;
+        uint32_t fails = 0u;    // bit 8*j + 7 - q: offset ob + 4*q + j failed the preamble test
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t d[2];
@@ -347,9 +346,11 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
                 d[h] = fail_bits<FMT>(lo, hi);
             }
             const uint32_t F = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
-            fails |= (F >> (7 - q)) & (0x01010101u << q);
+            // keep bits 7..8-q of every byte, take bit 7-q from F (select: one LOP3)
+            const uint32_t keep = 0x01010101u * (0xFFu & ~(0xFFu >> q));
+            fails = q == 0 ? F : ((fails & keep) | ((F >> q) & ~keep));
         }
-        const uint32_t hits = (~fails & 0x0F0F0F0Fu) << (4 * (it & 1));
+        const uint32_t hits = (~fails & 0xF0F0F0F0u) >> (4 * (it & 1));
         if (it < 2) pmA |= hits;
         else pmB |= hits;
     }
@@ -376,8 +377,8 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
-                const int it = 2 * half + ((b >> 2) & 1);
-                hitlist[pos++] = (uint16_t)(it * 512 + lane * 16 + 4 * (b & 3) + (b >> 3));
+                const int it = 2 * half + (((b >> 2) & 1) ^ 1);
+                hitlist[pos++] = (uint16_t)(it * 512 + lane * 16 + 4 * (3 - (b & 3)) + (b >> 3));
             }
         }
         __syncwarp();
@@ -404,8 +405,8 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            const int it = 2 * half + ((b >> 2) & 1);
-            const int o = 4 * (b & 3) + (b >> 3);
+            const int it = 2 * half + (((b >> 2) & 1) ^ 1);
+            const int o = 4 * (3 - (b & 3)) + (b >> 3);
             const int i = it * 512 + lane * 16 + o;
             if (i < wcands && df17_ok(lv, i)) c |= 1u << (16 * (it & 1) + o);
         }
@@ -430,7 +431,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
     }
 }
 
-template <int FMT>
+template <int FMT, bool kSingleSegment>
 __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams p)
 {
     // Warps never talk to each other: each owns one tile (kWarpTile candidate offsets), a
@@ -451,12 +452,12 @@ __global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams 
     const unsigned tile = blockIdx.x * kWarps + warp;
     if (tile >= p.n_tiles) return;
     unsigned seg = 0, tile_in_seg = tile;
-    if (p.tiles_per_seg < p.n_tiles) {
+    if (!kSingleSegment) {
         seg = tile / p.tiles_per_seg;
         tile_in_seg = tile - seg * p.tiles_per_seg;
     }
-    const unsigned long long seg_start = (unsigned long long)seg * p.seg_len;
-    const unsigned long long seg_n = min(p.seg_len, p.n_samples - seg_start);
+    const unsigned long long seg_start = kSingleSegment ? 0ull : (unsigned long long)seg * p.seg_len;
+    const unsigned long long seg_n = kSingleSegment ? p.n_samples : min(p.seg_len, p.n_samples - seg_start);
     const unsigned long long wpos = (unsigned long long)tile_in_seg * kWarpTile;
     const unsigned long long rem = seg_n > wpos ? seg_n - wpos : 0ull;
     const int wcands = rem > (unsigned long long)kFrameSamples
@@ -666,10 +667,14 @@ cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream
 {
     if (p.n_tiles == 0) return cudaSuccess;
     const unsigned grid = (p.n_tiles + kWarps - 1) / kWarps;
-    if (format == AIRGPU_FMT_U8)
-        decode_kernel<AIRGPU_FMT_U8><<<grid, kThreads, 0, stream>>>(p);
-    else
-        decode_kernel<AIRGPU_FMT_CS16><<<grid, kThreads, 0, stream>>>(p);
+    const bool single = p.tiles_per_seg >= p.n_tiles;     // one segment: no per-tile division
+    if (format == AIRGPU_FMT_U8) {
+        if (single) decode_kernel<AIRGPU_FMT_U8, true><<<grid, kThreads, 0, stream>>>(p);
+        else decode_kernel<AIRGPU_FMT_U8, false><<<grid, kThreads, 0, stream>>>(p);
+    } else {
+        if (single) decode_kernel<AIRGPU_FMT_CS16, true><<<grid, kThreads, 0, stream>>>(p);
+        else decode_kernel<AIRGPU_FMT_CS16, false><<<grid, kThreads, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
