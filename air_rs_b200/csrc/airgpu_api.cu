@@ -179,7 +179,6 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.n_tiles = g.n_tiles;
     p.base_offset = base;
     p.minus_one = 0xFFFFFFFFu;
-    p.k65536 = 65536u;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(d_iq) & 15u) == 0 && (g.n_tiles == g.tiles_per_seg || g.seg_len % 8 == 0)) ? 1u : 0u;
     p.scratch = c->scratch;
     p.cap = cap;
