@@ -297,47 +297,48 @@ __device__ __forceinline__ void emit_candidate(const uint16_t *lv, int i, int la
 template <int FMT>
 __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hitlist, int wcands, int lane, Sink &sink)
 {
-    // hit bits: iteration `it` lives in pmA (it 0-1) / pmB (it 2-3) at bit
-    // 8*j + 7 - 4*(it & 1) - q  <->  offset it*512 + lane*16 + 4*q + j
-    // (q = 0..3: which F register, j = 0..3: which byte of it)
-    uint32_t pmA = 0u, pmB = 0u;   // iterations 0-1, 2-3
-    // window chunks 2*lane + q of iteration `it` sit at padded chunk pc[q] + 72*it
+    // A lane owns 32 consecutive offsets per iteration (two iterations of 1024 offsets per
+    // tile): the shared min/max arrays are computed once for 16 offset pairs instead of 8.
+    // hit bits of iteration it (pmA: it 0, pmB: it 1): offset it*1024 + lane*32 + 4*q + j
+    // (q = 0..7: which F register, j = 0..3: which byte of it) is bit 8*j + 7 - (q & 3) - 4*(q >> 2).
+    uint32_t pmA = 0u, pmB = 0u;
+    // window chunks 4*lane + c of iteration `it` sit at padded chunk pc[c] + 144*it
     const uint4 *lv4 = reinterpret_cast<const uint4 *>(lv);
-    int pc[4];
+    int pc[6];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) pc[q] = phys_chunk(2 * lane + q);
+    for (int c = 0; c < 6; ++c) pc[c] = phys_chunk(4 * lane + c);
     // fully unrolled: shared-memory offsets and hit-bit positions become immediates
 #pragma unroll
-    for (int it = 0; it < kWarpTile / 512; ++it) {
-        if (it * 512 >= wcands) break;
-        // lane owns offsets [ob, ob+16); E[t] = (level[ob+2t], level[ob+2t+1])
-        uint32_t E[16];
+    for (int it = 0; it < kWarpTile / 1024; ++it) {
+        if (it * 1024 >= wcands) break;
+        // E[t] = (level[ob+2t], level[ob+2t+1]) with ob = it*1024 + lane*32
+        uint32_t E[24];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint4 v = lv4[pc[q] + 72 * it];
-            E[4 * q + 0] = v.x;
-            E[4 * q + 1] = v.y;
-            E[4 * q + 2] = v.z;
-            E[4 * q + 3] = v.w;
+        for (int c = 0; c < 6; ++c) {
+            const uint4 v = lv4[pc[c] + 144 * it];
+            E[4 * c + 0] = v.x;
+            E[4 * c + 1] = v.y;
+            E[4 * c + 2] = v.z;
+            E[4 * c + 3] = v.w;
         }
-        uint32_t O[15], ME[15], MO[10], W[13];
+        uint32_t O[23], ME[23], MO[18], W[21];
         // (measured alternative: O[t] on the FMA pipe via IMAD.WIDE + IMAD was slower, 0.633 vs 0.619 ms)
 #pragma unroll
-        for (int t = 0; t < 15; ++t) O[t] = __byte_perm(E[t], E[t + 1], 0x5432);   // (lvl[2t+1], lvl[2t+2])
+        for (int t = 0; t < 23; ++t) O[t] = __byte_perm(E[t], E[t + 1], 0x5432);   // (lvl[2t+1], lvl[2t+2])
 #pragma unroll
-        for (int t = 5; t < 15; ++t) ME[t] = __vminu2(E[t], O[t]);
+        for (int t = 5; t < 23; ++t) ME[t] = __vminu2(E[t], O[t]);
 #pragma unroll
-        for (int t = 1; t < 10; ++t) MO[t] = __vminu2(O[t], E[t + 1]);
+        for (int t = 1; t < 18; ++t) MO[t] = __vminu2(O[t], E[t + 1]);
 #pragma unroll
-        for (int t = 5; t < 13; ++t) W[t] = min3u2<FMT>(ME[t], ME[t + 1], ME[t + 2]);
+        for (int t = 5; t < 21; ++t) W[t] = min3u2<FMT>(ME[t], ME[t + 1], ME[t + 2]);
         // For the offset pair (ob+2t, ob+2t+1):
         //   highs 0,2,7,9               -> E[t], E[t+1], O[t+3], O[t+4]
         //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
-        // F[q] gathers the fail flags of four consecutive offsets (ob+4q .. ob+4q+3) into the
+        // F gathers the fail flags of four consecutive offsets (ob+4q .. ob+4q+3) into the
         // top bits of its four bytes.
-        uint32_t fails = 0u;    // bit 8*j + 7 - q: offset ob + 4*q + j failed the preamble test
+        uint32_t fails[2] = {0u, 0u};    // [q >> 2], bit 8*j + 7 - (q & 3): offset ob + 4*q + j failed
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
             uint32_t d[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -347,14 +348,16 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
                 d[h] = fail_bits<FMT>(lo, hi);
             }
             const uint32_t F = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
-            // keep bits 7..8-q of every byte, take bit 7-q from F (select: one LOP3)
-            const uint32_t keep = 0x01010101u * (0xFFu & ~(0xFFu >> q));
-            fails = q == 0 ? F : ((fails & keep) | ((F >> q) & ~keep));
+            // keep bits 7..8-r of every byte, take bit 7-r from F (select: one LOP3)
+            const int r = q & 3;
+            const uint32_t keep = 0x01010101u * (0xFFu & ~(0xFFu >> r));
+            fails[q >> 2] = r == 0 ? F : ((fails[q >> 2] & keep) | ((F >> r) & ~keep));
         }
-        const uint32_t hits = (~fails & 0xF0F0F0F0u) >> (4 * (it & 1));
-        if (it < 2) pmA |= hits;
-        else pmB |= hits;
+        const uint32_t hits = (~fails[0] & 0xF0F0F0F0u) | ((~fails[1] & 0xF0F0F0F0u) >> 4);
+        if (it == 0) pmA = hits;
+        else pmB = hits;
     }
+
     // ---- preamble hits of the whole tile ----
     const uint32_t nh = __popc(pmA) + __popc(pmB);
     const uint32_t total_hits = __reduce_add_sync(kFull, nh);
@@ -378,8 +381,8 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
-                const int it = 2 * half + (((b >> 2) & 1) ^ 1);
-                hitlist[pos++] = (uint16_t)(it * 512 + lane * 16 + 4 * (3 - (b & 3)) + (b >> 3));
+                const int o = 16 * (((b >> 2) & 1) ^ 1) + 4 * (3 - (b & 3)) + (b >> 3);
+                hitlist[pos++] = (uint16_t)(half * 1024 + lane * 32 + o);
             }
         }
         __syncwarp();
@@ -398,7 +401,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
     }
 
     // ---- many hits (degenerate input, e.g. a constant buffer): per-lane DF loops ----
-    uint32_t cmA = 0u, cmB = 0u;   // bit 16*(it & 1) + o: offset it*512 + lane*16 + o passes the gate (A: it 0-1, B: it 2-3)
+    uint32_t cmA = 0u, cmB = 0u;   // bit o: offset it*1024 + lane*32 + o passes the gate (A: it 0, B: it 1)
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         uint32_t m = half ? pmB : pmA;
@@ -406,18 +409,17 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            const int it = 2 * half + (((b >> 2) & 1) ^ 1);
-            const int o = 4 * (3 - (b & 3)) + (b >> 3);
-            const int i = it * 512 + lane * 16 + o;
-            if (i < wcands && df17_ok(lv, i)) c |= 1u << (16 * (it & 1) + o);
+            const int o = 16 * (((b >> 2) & 1) ^ 1) + 4 * (3 - (b & 3)) + (b >> 3);
+            const int i = half * 1024 + lane * 32 + o;
+            if (i < wcands && df17_ok(lv, i)) c |= 1u << o;
         }
         if (half) cmB = c;
         else cmA = c;
     }
     // survivors, in ascending offset order: iteration, then lane, then bit
 #pragma unroll 1
-    for (int it = 0; it < 4; ++it) {
-        const uint32_t mine = ((it < 2 ? cmA : cmB) >> (16 * (it & 1))) & 0xFFFFu;
+    for (int it = 0; it < 2; ++it) {
+        const uint32_t mine = it ? cmB : cmA;
         unsigned lanes = __ballot_sync(kFull, mine != 0u);
         while (lanes) {
             const int src_lane = __ffs(lanes) - 1;
@@ -426,7 +428,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
             while (bits) {
                 const int o = __ffs(bits) - 1;
                 bits &= bits - 1;
-                emit_candidate(lv, it * 512 + src_lane * 16 + o, lane, sink);
+                emit_candidate(lv, it * 1024 + src_lane * 32 + o, lane, sink);
             }
         }
     }
