@@ -434,8 +434,11 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
     }
 }
 
+#ifndef AIRGPU_MIN_CTAS
+#define AIRGPU_MIN_CTAS 8
+#endif
 template <int FMT, bool kSingleSegment>
-__global__ void __launch_bounds__(kThreads, 8) decode_kernel(const DecodeParams p)
+__global__ void __launch_bounds__(kThreads, AIRGPU_MIN_CTAS) decode_kernel(const DecodeParams p)
 {
     // Warps never talk to each other: each owns one tile (kWarpTile candidate offsets), a
     // private slice of shared memory, its own stage and its own output reservation.  The CTA
