@@ -624,34 +624,46 @@ __global__ void __launch_bounds__(kGroupTiles)
 gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const unsigned long long *group_base,
               unsigned n_tiles, unsigned long long *out, unsigned long long cap, unsigned long long ovf_cap)
 {
+    // One CTA per group of kGroupTiles tiles: scan the counts in shared memory, then one
+    // THREAD per output record (binary search for its tile) so that all record copies of the
+    // group are independent loads in flight at once.
     __shared__ unsigned long long s_warp[33];
-    __shared__ unsigned long long s_pos[kGroupTiles];
-    __shared__ uint2 s_tab[kGroupTiles];
+    __shared__ unsigned int s_excl[kGroupTiles + 1];
+    __shared__ unsigned int s_ovf[kGroupTiles];
     const unsigned t0 = blockIdx.x * kGroupTiles;
     const unsigned t = t0 + threadIdx.x;
     const uint2 e = t < n_tiles ? tile_tab[t] : make_uint2(0u, 0u);
     unsigned long long total;
     const unsigned long long excl = block_exclusive_scan(e.y, s_warp, &total);
     if (total == 0) return;
-    s_pos[threadIdx.x] = group_base[blockIdx.x] + excl;
-    s_tab[threadIdx.x] = e;
+    s_excl[threadIdx.x] = (unsigned)excl;
+    s_ovf[threadIdx.x] = e.x;
+    if (threadIdx.x == 0) s_excl[kGroupTiles] = (unsigned)total;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int k = warp; k < kGroupTiles; k += nwarps) {
-        const uint2 ek = s_tab[k];
-        if (ek.y == 0) continue;
-        const unsigned long long pos = s_pos[k];
-        const unsigned long long slot0 = (unsigned long long)(t0 + k) * kSlotsPerTile;
-        const unsigned long long ovf0 = (unsigned long long)n_tiles * kSlotsPerTile + ek.x;
-        for (unsigned q = lane; q < ek.y * 3; q += 32) {
-            const unsigned r = q / 3;
-            const unsigned long long dst = pos + r;
-            if (dst >= cap) continue;
-            if (r < (unsigned)kSlotsPerTile)
-                out[dst * 3 + q % 3] = scratch[(slot0 + r) * 3 + q % 3];
-            else if ((unsigned long long)ek.x + (r - kSlotsPerTile) < ovf_cap)
-                out[dst * 3 + q % 3] = scratch[(ovf0 + (r - kSlotsPerTile)) * 3 + q % 3];
+    const unsigned long long gbase = group_base[blockIdx.x];
+    for (unsigned r = threadIdx.x; r < (unsigned)total; r += kGroupTiles) {
+        // largest k with s_excl[k] <= r (tiles with zero frames share their successor's value)
+        unsigned lo = 0, hi = kGroupTiles;
+        while (hi - lo > 1) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (s_excl[mid] <= r) lo = mid;
+            else hi = mid;
         }
+        const unsigned idx = r - s_excl[lo];
+        const unsigned long long dst = gbase + r;
+        if (dst >= cap) continue;
+        unsigned long long src;
+        if (idx < (unsigned)kSlotsPerTile) {
+            src = (unsigned long long)(t0 + lo) * kSlotsPerTile + idx;
+        } else {
+            const unsigned long long o = (unsigned long long)s_ovf[lo] + (idx - kSlotsPerTile);
+            if (o >= ovf_cap) continue;
+            src = (unsigned long long)n_tiles * kSlotsPerTile + o;
+        }
+        const unsigned long long w0 = scratch[src * 3 + 0], w1 = scratch[src * 3 + 1], w2 = scratch[src * 3 + 2];
+        out[dst * 3 + 0] = w0;
+        out[dst * 3 + 1] = w1;
+        out[dst * 3 + 2] = w2;
     }
 }
 
