@@ -235,9 +235,11 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = 2.0 * n_local + 24.0 * n_frames_local
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None      # dram__bytes_read + write of one launch, from the committed ncu capture of this workload
     try:
-        traffic = json.loads((ROOT / "profiles" / "latest_traffic.json").read_text()).get("dram_bytes_per_launch")
+        tj = json.loads((ROOT / "profiles" / "latest_traffic.json").read_text())
+        if int(tj.get("n_samples", -1)) == int(n_local):
+            traffic = tj.get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {
