@@ -74,13 +74,15 @@ class ShardedDecoder:
     """Decode one rank's shard in `pieces` sub-shards and all-gather the frame lists over NCCL
     without ever stalling the GPU on the host.
 
-    The exchange of a piece is two collectives on a high-priority stream: the counts, then
-    the records truncated to `slab` rows per rank.  `slab` is not the worst-case capacity but
-    what the traffic actually needs (a little above the largest count seen so far, the same
-    on every rank because every rank sees all counts); `finish()` checks after the fact that
-    no rank produced more than `slab` frames and repeats the exchange with a larger slab if
-    one did.  So the steady state has no host synchronisation between steps, the decode of
-    piece p+1 overlaps the exchange of piece p, and only the real frames (+ ~15 %) cross NVLink.
+    The exchange of a piece is ONE collective on a high-priority stream: each rank's buffer
+    starts with a 24-byte header whose first 8 bytes are the frame count (the library writes
+    the count there itself: `d_count` of airgpu_decode_device points at it), followed by the
+    records, truncated to `slab` rows.  `slab` is not the worst-case capacity but what the
+    traffic actually needs (a little above the largest count seen so far, the same on every
+    rank because every rank sees all counts); `finish()` checks after the fact that no rank
+    produced more than `slab` frames and repeats the exchange with a larger slab if one did.
+    So the steady state has no host synchronisation between steps, the decode of piece p+1
+    overlaps the exchange of piece p, and only the real frames (+ ~15 %) cross NVLink.
     Result order: rank-major, piece-minor == ascending offset == the reference's order.
     """
 
@@ -102,11 +104,10 @@ class ShardedDecoder:
         self.cap = cap
         self.slab = cap                      # rows exchanged per rank and piece; shrinks after the first step
         P, W = len(self.ranges), self.world
-        self.out = [torch.empty((cap, RECORD_BYTES), dtype=torch.uint8, device=self.dev) for _ in range(P)]
-        self.cnt = torch.zeros((P, 1), dtype=torch.int64, device=self.dev)
-        self.cnt_all = torch.zeros((P, W), dtype=torch.int64, device=self.dev)
-        self.cnt_host = torch.zeros((P, W), dtype=torch.int64).pin_memory()
+        # row 0 = header (frame count in its first 8 bytes), rows 1.. = records
+        self.out = [torch.zeros((cap + 1, RECORD_BYTES), dtype=torch.uint8, device=self.dev) for _ in range(P)]
         self.gath = None
+        self.hdr_host = torch.zeros((P, W), dtype=torch.int64).pin_memory()
         # high priority: NCCL's few CTAs must get SM slots while the decode kernel still has CTAs queued
         self.comm = torch.cuda.Stream(device=self.dev, priority=-1)
         self.decoded = [torch.cuda.Event() for _ in range(P)]
@@ -117,12 +118,25 @@ class ShardedDecoder:
         import torch
 
         P, W = len(self.ranges), self.world
-        self.gath = [torch.empty((W, self.slab, RECORD_BYTES), dtype=torch.uint8, device=self.dev) for _ in range(P)]
+        self.gath = [torch.empty((W, self.slab + 1, RECORD_BYTES), dtype=torch.uint8, device=self.dev)
+                     for _ in range(P)]
+
+    def _exchange(self, k):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gath[k].view(-1), self.out[k][: self.slab + 1].reshape(-1),
+                                        group=self.group)
+        else:
+            self.gath[k][0].copy_(self.out[k][: self.slab + 1])
+        # counts of all ranks for this piece -> pinned host memory (read in finish())
+        self.hdr_host[k].copy_(self.gath[k][:, 0, :8].contiguous().view(-1).view(dtype=self.hdr_host.dtype),
+                               non_blocking=True)
+        self.gathered[k].record(self.comm)
 
     def step(self, iq, bytes_per_sample: int = 2):
         """Queue one pass over this rank's shard (CUDA tensor of interleaved IQ).  Asynchronous."""
         import torch
-        import torch.distributed as dist
 
         if self.gath is None:
             self._alloc()
@@ -131,29 +145,22 @@ class ShardedDecoder:
         for k, (s, e) in enumerate(self.ranges):
             if not self._first_step:
                 compute.wait_event(self.gathered[k])     # out[k] of the previous step has been sent
-            self.dec.decode_device(base_ptr + s * bytes_per_sample, e - s + HALO, self.out[k].data_ptr(), self.cap,
-                                   0, self.first + s, self.cnt[k].data_ptr(), compute.cuda_stream)
+            o = self.out[k]
+            self.dec.decode_device(base_ptr + s * bytes_per_sample, e - s + HALO, o.data_ptr() + RECORD_BYTES,
+                                   self.cap, 0, self.first + s, o.data_ptr(), compute.cuda_stream)
             self.decoded[k].record(compute)
         self._first_step = False
         with torch.cuda.stream(self.comm):
             for k in range(len(self.ranges)):
                 self.comm.wait_event(self.decoded[k])
-                if self.world > 1:
-                    dist.all_gather_into_tensor(self.cnt_all[k], self.cnt[k], group=self.group)
-                    dist.all_gather_into_tensor(self.gath[k].view(-1), self.out[k][: self.slab].reshape(-1),
-                                                group=self.group)
-                else:
-                    self.cnt_all[k].copy_(self.cnt[k])
-                    self.gath[k][0].copy_(self.out[k][: self.slab])
-                self.gathered[k].record(self.comm)
-            self.cnt_host.copy_(self.cnt_all, non_blocking=True)
+                self._exchange(k)
 
     def finish(self, concat: bool = True):
         """Wait for the last queued step; returns (frames [n, 24] in global order, n)."""
         import torch
 
         self.comm.synchronize()
-        counts = self.cnt_host.clone()
+        counts = self.hdr_host.clone()
         m = int(counts.max())
         if m > self.cap:
             raise ValueError(f"a sub-shard produced {m} frames but the buffers hold {self.cap}")
@@ -161,30 +168,19 @@ class ShardedDecoder:
             # optimistic slab was too small (traffic got denser): exchange again with room to spare
             self.slab = min(self.cap, (int(m * 1.25) + 1023) // 1024 * 1024)
             self._alloc()
-            self._regather()
-            counts = self.cnt_host.clone()
+            with torch.cuda.stream(self.comm):
+                for k in range(len(self.ranges)):
+                    self._exchange(k)
+            self.comm.synchronize()
+            counts = self.hdr_host.clone()
         elif self.slab == self.cap and m < self.cap:
             self.slab = min(self.cap, (int(m * 1.15) + 1023) // 1024 * 1024)   # first step done: size for the traffic
             keep = self.gath
-            self.gath = [g[:, : self.slab].contiguous() for g in keep]
+            self.gath = [g[:, : self.slab + 1].contiguous() for g in keep]
         parts, total = [], 0
         for r in range(self.world):
             for k in range(len(self.ranges)):
                 c = int(counts[k, r])
-                parts.append(self.gath[k][r, :c])
+                parts.append(self.gath[k][r, 1 : 1 + c])
                 total += c
         return (torch.cat(parts) if concat else parts), total
-
-    def _regather(self):
-        import torch
-        import torch.distributed as dist
-
-        with torch.cuda.stream(self.comm):
-            for k in range(len(self.ranges)):
-                if self.world > 1:
-                    dist.all_gather_into_tensor(self.gath[k].view(-1), self.out[k][: self.slab].reshape(-1),
-                                                group=self.group)
-                else:
-                    self.gath[k][0].copy_(self.out[k][: self.slab])
-                self.gathered[k].record(self.comm)
-        self.comm.synchronize()
