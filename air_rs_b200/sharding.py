@@ -71,68 +71,110 @@ def concat_gathered(slab, counts):
 
 
 class ShardedDecoder:
-    """Decode one rank's shard in `pieces` sub-shards and all-gather the frame lists over NCCL
-    without ever stalling the GPU on the host.
+    """Decode one rank's shard in `pieces` sub-shards and exchange the frame lists with every
+    other rank without ever stalling the GPU on the host.
 
-    The exchange of a piece is ONE collective on a high-priority stream: each rank's buffer
-    starts with a 24-byte header whose first 8 bytes are the frame count (the library writes
-    the count there itself: `d_count` of airgpu_decode_device points at it), followed by the
-    records, truncated to `slab` rows.  `slab` is not the worst-case capacity but what the
-    traffic actually needs (a little above the largest count seen so far, the same on every
-    rank because every rank sees all counts); `finish()` checks after the fact that no rank
-    produced more than `slab` frames and repeats the exchange with a larger slab if one did.
-    So the steady state has no host synchronisation between steps, the decode of piece p+1
-    overlaps the exchange of piece p, and only the real frames (+ ~15 %) cross NVLink.
+    Each rank's buffer for a piece starts with a 24-byte header whose first 8 bytes are the
+    frame count (the library writes it there itself: `d_count` of airgpu_decode_device points
+    at it), followed by the ordered records.  Only `slab` rows travel: not the worst-case
+    capacity but what the traffic needs (a little above the largest count seen so far, the
+    same on every rank because every rank sees all counts); `finish()` checks after the fact
+    that no rank produced more and repeats the exchange with more rows if one did.
+
+    Two exchange back ends:
+      "p2p"  (default on NVLink boxes) -- every rank owns a symmetric-memory slab set
+             (torch.distributed._symmetric_memory, rendezvous over the NCCL group); a rank
+             copies its rows straight into its slot of every peer's slabs with plain device
+             copies on a high-priority stream, i.e. over NVLink by the copy engines, so the
+             exchange takes no SMs away from the decode kernel of the next piece.  One
+             symmetric-memory barrier per step makes the peers' writes visible.
+      "nccl" -- one ncclAllGather per piece (used by the CPU/gloo tests and as the fallback).
     Result order: rank-major, piece-minor == ascending offset == the reference's order.
     """
 
     def __init__(self, decoder, n_local: int, first_sample: int, pieces: int = 2, cap_per_piece: int = 0,
-                 group=None):
+                 group=None, exchange: str = "auto"):
         import torch
         import torch.distributed as dist
 
         self.dec = decoder
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.dev = torch.device("cuda", decoder.device)
         cands = max(0, n_local - HALO)
         pieces = max(1, min(pieces, max(1, cands // ALIGN)))
         b = [min(cands, (cands * k // pieces) // ALIGN * ALIGN) for k in range(pieces)] + [cands]
-        self.ranges = [(b[k], b[k + 1]) for k in range(pieces)]   # same number of collectives on every rank
+        self.ranges = [(b[k], b[k + 1]) for k in range(pieces)]   # same number of exchanges on every rank
         self.first = first_sample
         cap = cap_per_piece or max(1 << 14, (max(e - s for s, e in self.ranges) + HALO) // 200)   # ~4x dense traffic
+        if self.world > 1:   # every rank must use the same row count
+            c = torch.tensor([cap], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(c, op=dist.ReduceOp.MAX, group=group)
+            cap = int(c.item())
         self.cap = cap
         self.slab = cap                      # rows exchanged per rank and piece; shrinks after the first step
         P, W = len(self.ranges), self.world
         # row 0 = header (frame count in its first 8 bytes), rows 1.. = records
         self.out = [torch.zeros((cap + 1, RECORD_BYTES), dtype=torch.uint8, device=self.dev) for _ in range(P)]
-        self.gath = None
         self.hdr_host = torch.zeros((P, W), dtype=torch.int64).pin_memory()
-        # high priority: NCCL's few CTAs must get SM slots while the decode kernel still has CTAs queued
+        # high priority: the exchange must get going while the decode kernel still has CTAs queued
         self.comm = torch.cuda.Stream(device=self.dev, priority=-1)
         self.decoded = [torch.cuda.Event() for _ in range(P)]
         self.gathered = [torch.cuda.Event() for _ in range(P)]
         self._first_step = True
+        self.exchange = "nccl"
+        self.symm = None
+        self.gath = None
+        if exchange in ("auto", "p2p") and self.world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                rows = P * W * (cap + 1)
+                self._symm_t = symm.empty(rows * RECORD_BYTES, dtype=torch.uint8, device=self.dev)
+                g = group if group is not None else dist.group.WORLD
+                self.symm = symm.rendezvous(self._symm_t, g.group_name)
+                self.gath_full = self._symm_t.view(P, W, cap + 1, RECORD_BYTES)
+                self.peer_slots = [
+                    [self.symm.get_buffer(q, (P, W, cap + 1, RECORD_BYTES), torch.uint8)[k][self.rank]
+                     for k in range(P)] for q in range(W)]
+                self.exchange = "p2p"
+            except Exception:
+                if exchange == "p2p":
+                    raise
+                self.symm = None
 
     def _alloc(self):
         import torch
 
         P, W = len(self.ranges), self.world
-        self.gath = [torch.empty((W, self.slab + 1, RECORD_BYTES), dtype=torch.uint8, device=self.dev)
-                     for _ in range(P)]
+        if self.exchange == "p2p":
+            self.gath = [self.gath_full[k] for k in range(P)]
+        else:
+            self.gath = [torch.empty((W, self.slab + 1, RECORD_BYTES), dtype=torch.uint8, device=self.dev)
+                         for _ in range(P)]
 
     def _exchange(self, k):
         import torch.distributed as dist
 
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.gath[k].view(-1), self.out[k][: self.slab + 1].reshape(-1),
-                                        group=self.group)
+        rows = self.slab + 1
+        if self.exchange == "p2p":
+            for q in range(self.world):      # my rows -> my slot in every rank's slab set (NVLink copy engines)
+                self.peer_slots[(self.rank + q) % self.world][k][:rows].copy_(self.out[k][:rows], non_blocking=True)
+        elif self.world > 1:
+            dist.all_gather_into_tensor(self.gath[k].view(-1), self.out[k][:rows].reshape(-1), group=self.group)
         else:
-            self.gath[k][0].copy_(self.out[k][: self.slab + 1])
-        # counts of all ranks for this piece -> pinned host memory (read in finish())
-        self.hdr_host[k].copy_(self.gath[k][:, 0, :8].contiguous().view(-1).view(dtype=self.hdr_host.dtype),
-                               non_blocking=True)
+            self.gath[k][0].copy_(self.out[k][:rows])
         self.gathered[k].record(self.comm)
+
+    def _publish_counts(self):
+        """After every piece of a step has been exchanged: barrier (p2p), then the counts of all ranks
+        go to pinned host memory for finish()."""
+        if self.exchange == "p2p":
+            self.symm.barrier(channel=0)
+        for k in range(len(self.ranges)):
+            self.hdr_host[k].copy_(self.gath[k][:, 0, :8].contiguous().view(-1).view(dtype=self.hdr_host.dtype),
+                                   non_blocking=True)
 
     def step(self, iq, bytes_per_sample: int = 2):
         """Queue one pass over this rank's shard (CUDA tensor of interleaved IQ).  Asynchronous."""
@@ -154,6 +196,7 @@ class ShardedDecoder:
             for k in range(len(self.ranges)):
                 self.comm.wait_event(self.decoded[k])
                 self._exchange(k)
+            self._publish_counts()
 
     def finish(self, concat: bool = True):
         """Wait for the last queued step; returns (frames [n, 24] in global order, n)."""
@@ -165,18 +208,21 @@ class ShardedDecoder:
         if m > self.cap:
             raise ValueError(f"a sub-shard produced {m} frames but the buffers hold {self.cap}")
         if m > self.slab:
-            # optimistic slab was too small (traffic got denser): exchange again with room to spare
+            # optimistic row count was too small (traffic got denser): exchange again with room to spare
             self.slab = min(self.cap, (int(m * 1.25) + 1023) // 1024 * 1024)
-            self._alloc()
+            if self.exchange != "p2p":
+                self._alloc()
             with torch.cuda.stream(self.comm):
                 for k in range(len(self.ranges)):
                     self._exchange(k)
+                self._publish_counts()
             self.comm.synchronize()
             counts = self.hdr_host.clone()
         elif self.slab == self.cap and m < self.cap:
             self.slab = min(self.cap, (int(m * 1.15) + 1023) // 1024 * 1024)   # first step done: size for the traffic
-            keep = self.gath
-            self.gath = [g[:, : self.slab + 1].contiguous() for g in keep]
+            if self.exchange != "p2p":
+                keep = self.gath
+                self.gath = [g[:, : self.slab + 1].contiguous() for g in keep]
         parts, total = [], 0
         for r in range(self.world):
             for k in range(len(self.ranges)):

@@ -157,7 +157,8 @@ def run_ours(args):
     assert stream != 0
     state = {"frames": 0, "gathered": None}
     pieces = 1 if world == 1 else int(os.environ.get("AIRGPU_PIECES", 2))
-    sharded = sharding.ShardedDecoder(dec, n_local, a, pieces=pieces) if world > 1 else None
+    sharded = (sharding.ShardedDecoder(dec, n_local, a, pieces=pieces, exchange=os.environ.get("AIRGPU_EXCHANGE", "auto"))
+               if world > 1 else None)
 
     def decode_resident():
         dec.decode_device(iq.data_ptr(), n_local, out.data_ptr(), cap, 0, a, d_count.data_ptr(), stream)
@@ -328,6 +329,7 @@ def run_ours(args):
             "frames_per_step": state["frames"],
             "gpu_launches": 3 * args.steps * pieces,
             "pieces_per_rank": pieces,
+            "frame_exchange": (sharded.exchange if sharded is not None else None),
             "kernels_per_step": ["decode_kernel<U8>", "group_scan_kernel", "gather_kernel"],
             "clocks": sampler.summary(),
             "roofline": roofline,
