@@ -213,8 +213,21 @@ def run_ours(args):
     ms_total = timed(step, args.steps, args.warmup, sampler)
     sampler.stop()
     ms_step = ms_total / args.steps
+    exchange_ok = None
     if world > 1:
         decode_resident()                       # whole local shard once more, for the per-rank frame count
+        torch.cuda.synchronize()
+        # integrity of the exchange: checksums of the gathered list == sum over ranks of local checksums
+        nl = int(d_count.item())
+        loc = out[:nl].contiguous()
+        chk = torch.stack([loc[:, 16:24].contiguous().view(torch.int64).sum(),
+                           loc[:, :16].to(torch.int64).sum(), torch.tensor(nl, device=dev)])
+        dist.all_reduce(chk)
+        g = state["gathered"]
+        got = torch.stack([g[:, 16:24].contiguous().view(torch.int64).sum(), g[:, :16].to(torch.int64).sum(),
+                           torch.tensor(g.shape[0], device=dev)])
+        offs = g[:, 16:24].contiguous().view(torch.int64).view(-1)
+        exchange_ok = bool(torch.equal(chk, got)) and bool((offs[1:] > offs[:-1]).all()) if g.shape[0] > 1 else bool(torch.equal(chk, got))
     n_frames_local = int(d_count.item())
     if world == 1:
         state["frames"] = n_frames_local
@@ -330,6 +343,7 @@ def run_ours(args):
             "gpu_launches": 3 * args.steps * pieces,
             "pieces_per_rank": pieces,
             "frame_exchange": (sharded.exchange if sharded is not None else None),
+            "gathered_list_checks_out": exchange_ok,
             "kernels_per_step": ["decode_kernel<U8>", "group_scan_kernel", "gather_kernel"],
             "clocks": sampler.summary(),
             "roofline": roofline,
