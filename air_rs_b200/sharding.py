@@ -123,9 +123,6 @@ class ShardedDecoder:
         self.decoded = [torch.cuda.Event() for _ in range(P)]
         self.gathered = [torch.cuda.Event() for _ in range(P)]
         self._first_step = True
-        # one extra stream per peer: the copies to different peers run on different copy engines
-        self.peer_streams = [torch.cuda.Stream(device=self.dev, priority=-1) for _ in range(max(0, self.world - 1))]
-        self.copied = [[torch.cuda.Event() for _ in range(max(0, self.world - 1))] for _ in range(P)]
         self.exchange = "nccl"
         self.symm = None
         self.gath = None
@@ -162,19 +159,8 @@ class ShardedDecoder:
 
         rows = self.slab + 1
         if self.exchange == "p2p":
-            import torch
-
-            # my rows -> my slot in every rank's slab set: plain device copies over NVLink, one stream per peer
-            for q in range(1, self.world):
-                st = self.peer_streams[q - 1]
-                st.wait_event(self.decoded[k])
-                with torch.cuda.stream(st):
-                    self.peer_slots[(self.rank + q) % self.world][k][:rows].copy_(self.out[k][:rows],
-                                                                                 non_blocking=True)
-                    self.copied[k][q - 1].record(st)
-            self.peer_slots[self.rank][k][:rows].copy_(self.out[k][:rows], non_blocking=True)
-            for q in range(1, self.world):
-                self.comm.wait_event(self.copied[k][q - 1])
+            for q in range(self.world):      # my rows -> my slot in every rank's slab set (NVLink copy engines)
+                self.peer_slots[(self.rank + q) % self.world][k][:rows].copy_(self.out[k][:rows], non_blocking=True)
         elif self.world > 1:
             dist.all_gather_into_tensor(self.gath[k].view(-1), self.out[k][:rows].reshape(-1), group=self.group)
         else:
