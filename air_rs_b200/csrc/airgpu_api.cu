@@ -82,13 +82,13 @@ struct airgpu_ctx {
     size_t max_frames = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr, ev_sync = nullptr, evk0 = nullptr, evk1 = nullptr;
-    bool ev_valid = false, evh_valid = false, evk_valid = false;
+    bool ev_valid = false, evh_valid = false, evk_valid = false, sync_valid = false;
 
     // workspace shared by every decode on the compute stream (stream-ordered reuse)
     airgpu_frame *scratch = nullptr;
     size_t scratch_cap = 0;
     uint2 *tile_tab = nullptr;
-    unsigned long long *group_sum = nullptr;   // 3 * groups_cap: frame sums, gate sums, bases
+    unsigned long long *group_sum = nullptr;   // [overflow counter | frame sums | gate sums | bases], 1 + 3 * groups_cap
     size_t groups_cap = 0;
     size_t tiles_cap = 0;
     unsigned long long *counters = nullptr;   // kNumCounters + 1 (last = running frame total)
@@ -121,7 +121,7 @@ int ensure_tiles(airgpu_ctx *c, size_t n_tiles)
     size_t want = std::max<size_t>(n_tiles, 1024);
     size_t groups = (want + kGroupTiles - 1) / kGroupTiles;
     CU(cudaMalloc(&c->tile_tab, want * sizeof(uint2)));
-    CU(cudaMalloc(&c->group_sum, 3 * groups * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->group_sum, (1 + 3 * groups) * sizeof(unsigned long long)));
     c->tiles_cap = want;
     c->groups_cap = groups;
     return AIRGPU_OK;
@@ -166,10 +166,8 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     const size_t ovf_cap = std::max<size_t>(cap, 1);
     if ((rc = ensure_scratch(c, (size_t)g.n_tiles * kSlotsPerTile + ovf_cap)) != AIRGPU_OK) return rc;
 
-    // the overflow index and the per-group sums restart with every piece
-    CU(cudaMemsetAsync(c->counters + kCounterOverflow, 0, sizeof(unsigned long long), stream));
-    const size_t n_groups = (g.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    if (n_groups) CU(cudaMemsetAsync(c->group_sum, 0, 2 * c->groups_cap * sizeof(unsigned long long), stream));
+    // the overflow index and the per-group sums restart with every piece (one memset: they are adjacent)
+    CU(cudaMemsetAsync(c->group_sum, 0, (1 + 2 * c->groups_cap) * sizeof(unsigned long long), stream));
 
     DecodeParams p{};
     p.iq = d_iq;
@@ -185,9 +183,10 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.ovf_cap = ovf_cap;
     p.counters = c->counters;
     p.tile_tab = c->tile_tab;
-    p.group_sum = c->group_sum;
-    p.group_gate = c->group_sum + c->groups_cap;
-    p.group_base = c->group_sum + 2 * c->groups_cap;
+    p.ovf_counter = c->group_sum;
+    p.group_sum = c->group_sum + 1;
+    p.group_gate = c->group_sum + 1 + c->groups_cap;
+    p.group_base = c->group_sum + 1 + 2 * c->groups_cap;
     CU(cudaEventRecord(c->evk0, stream));
     CU(launch_decode(c->format, p, stream));
     CU(cudaEventRecord(c->evk1, stream));
@@ -361,17 +360,24 @@ int airgpu_decode_device(airgpu_ctx *c, const void *d_iq, size_t n_samples, size
     CU(cudaEventRecord(c->ev1, s));
     c->ev_valid = true;
     c->evh_valid = false;
-    // mirror the counters for airgpu_sync_count / airgpu_get_stats
-    CU(cudaMemcpyAsync(c->h_counters, c->counters, kNumCounters * sizeof(unsigned long long),
-                       cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(c->h_counters + kNumCounters, total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(c->ev_sync, s));
+    if (!d_count) {
+        // mirror the counters for airgpu_sync_count (a caller that passes d_count reads it itself)
+        CU(cudaMemcpyAsync(c->h_counters, c->counters, kNumCounters * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(c->h_counters + kNumCounters, total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(c->ev_sync, s));
+        c->sync_valid = true;
+    } else {
+        c->sync_valid = false;
+    }
     return AIRGPU_OK;
 }
 
 int airgpu_sync_count(airgpu_ctx *c, uint64_t *n_frames)
 {
     if (!c) return fail(AIRGPU_ERR_INVALID, "ctx is NULL");
+    if (!c->sync_valid)
+        return fail(AIRGPU_ERR_INVALID, "airgpu_sync_count: the last airgpu_decode_device was given d_count; read the count there");
     CU(cudaSetDevice(c->device));
     CU(cudaEventSynchronize(c->ev_sync));
     if (n_frames) *n_frames = c->h_counters[kNumCounters];

@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, AIRGPU_MIN_CTAS) decode_kernel(const
         if (nvalid) atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)nvalid);            // RED
         if (sink.gate) atomicAdd(&p.group_gate[tile / kGroupTiles], (unsigned long long)sink.gate);    // RED
         if (nvalid > (uint32_t)kSlotsPerTile)
-            ovf_base = atomicAdd(&p.counters[kCounterOverflow], (unsigned long long)(nvalid - kSlotsPerTile));
+            ovf_base = atomicAdd(p.ovf_counter, (unsigned long long)(nvalid - kSlotsPerTile));
         p.tile_tab[tile] = make_uint2((unsigned)min(ovf_base, 0xFFFFFFFFull), nvalid);
     }
     if (nvalid > (uint32_t)kSlotsPerTile) {

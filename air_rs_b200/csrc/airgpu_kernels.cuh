@@ -40,13 +40,14 @@ struct DecodeParams {
     unsigned long long cap;         // capacity of the final output
     unsigned long long ovf_cap;     // capacity of the overflow area
     unsigned long long *counters;   // see the enum below
+    unsigned long long *ovf_counter; // next free record of the overflow area (zeroed before the launch)
     uint2 *tile_tab;                // per tile: (overflow base, frame count)
     unsigned long long *group_sum;  // per group of kGroupTiles tiles: frames (zeroed before the launch)
     unsigned long long *group_gate; // per group: gate passes (zeroed before the launch)
     unsigned long long *group_base; // per group: ordered position of its first frame
 };
 
-enum { kCounterOverflow = 0, kCounterGate = 1, kNumCounters = 4 };
+enum { kCounterGate = 1, kNumCounters = 4 };
 
 // Launchers (stream-ordered, no synchronisation inside).
 cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream);

@@ -132,8 +132,9 @@ int airgpu_decode(airgpu_ctx *ctx, const void *iq, size_t n_samples,
 /* ---- decode of a capture already resident in DEVICE memory --------------- *
  * d_iq and d_out are device pointers on the context's device; d_out holds
  * `cap` records.  `stream` is a cudaStream_t (NULL = the context's compute
- * stream).  Asynchronous: the frame count lands in *d_count (device, 8 bytes)
- * and is also returned by airgpu_sync_count() after the stream is drained.
+ * stream).  Asynchronous: the frame count lands in *d_count (device, 8 bytes);
+ * with d_count == NULL it is kept by the library and airgpu_sync_count() waits
+ * for the decode and returns it.
  * Shards of a long capture call this once per GPU with base_offset = first
  * sample of the shard and n_samples including the 240-sample right halo. */
 int airgpu_decode_device(airgpu_ctx *ctx, const void *d_iq, size_t n_samples,
