@@ -48,16 +48,23 @@ METRIC = "Msamples/s IQ->CRC-valid frames"
 UNIT = "Msamples/s"
 
 
+TRAFFIC = os.environ.get("AIRGPU_TRAFFIC", "dense")   # "sparse" = config 1's density (supplementary runs only)
+
+
 def traffic_table():
     from air_rs_b200 import synth
 
+    if TRAFFIC == "sparse":
+        return synth.make_traffic(SEED, PERIOD, df17_per_s=200.0, decoy_per_s=0.0, snr_db=(20.0, 20.0), sigma=SIGMA)
     return synth.make_traffic(SEED, PERIOD, df17_per_s=3000.0, decoy_per_s=3000.0, snr_db=(8.0, 30.0), sigma=SIGMA)
 
 
 def workload_config(n_gpus: int, total: int) -> dict:
     return {
-        "workload": f"config5: 1 h synthetic capture, {total} samples u8 IQ ({2 * total / 1e9:.2f} GB), dense traffic "
-                    "(3000 DF17/s + 3000 decoys/s, SNR 8-30 dB, 10 s schedule repeated, noise never repeats), "
+        "workload": f"config5: 1 h synthetic capture, {total} samples u8 IQ ({2 * total / 1e9:.2f} GB), "
+                    + ("dense traffic (3000 DF17/s + 3000 decoys/s, SNR 8-30 dB" if TRAFFIC != "sparse"
+                       else "SPARSE traffic (config 1 density: 200 DF17/s at 20 dB") +
+                    ", 10 s schedule repeated, noise never repeats), "
                     "frames modulated at the reference's fixed 2 samples/us",
         "format": "u8",
         "mode": "continuous",
