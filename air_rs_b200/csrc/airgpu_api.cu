@@ -7,7 +7,6 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -179,14 +178,6 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.base_offset = base;
     p.minus_one = 0xFFFFFFFFu;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(d_iq) & 15u) == 0 && (g.n_tiles == g.tiles_per_seg || g.seg_len % 8 == 0)) ? 1u : 0u;
-    {
-        static int pf = -1;
-        if (pf < 0) {
-            const char *e = getenv("AIRGPU_PREFETCH_TILES");
-            pf = e ? atoi(e) : 0;
-        }
-        p.prefetch_tiles = p.vec_ok ? (unsigned)pf : 0u;
-    }
     p.scratch = c->scratch;
     p.cap = cap;
     p.ovf_cap = ovf_cap;

@@ -484,13 +484,6 @@ __global__ void __launch_bounds__(kThreads, AIRGPU_MIN_CTAS) decode_kernel(const
 
     // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
     const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
-    // Pull the samples of a tile a few waves ahead into L2 with one bulk prefetch, so that the
-    // loads of that tile's warp see L2 latency instead of HBM latency (tiles are scheduled in
-    // index order; one instruction per 4 KB).
-    if (kSingleSegment && lane == 0 && p.prefetch_tiles && tile + p.prefetch_tiles < p.n_tiles - 1) {
-        const uint8_t *ahead = src + (unsigned long long)p.prefetch_tiles * (kWarpTile * BPS);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ahead), "n"(kWarpTile * BPS) : "memory");
-    }
     if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
         // 9 chunks per lane in three batches; the loads of batch g+1 are in flight while
         // batch g is converted, so a warp waits for HBM once per tile, not three times

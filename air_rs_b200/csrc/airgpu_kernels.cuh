@@ -34,7 +34,6 @@ struct DecodeParams {
     unsigned int tiles_per_seg;
     unsigned int n_tiles;           // n_segments * tiles_per_seg
     unsigned int minus_one;         // 0xFFFFFFFF (see levels_u8_pair)
-    unsigned int prefetch_tiles;    // L2 prefetch distance in tiles (0 = off)
     unsigned int vec_ok;            // every warp slice starts 16-byte aligned (base aligned, seg_len % 8 == 0)
     unsigned long long base_offset; // added to every frame offset
     airgpu_frame *scratch;          // n_tiles * kSlotsPerTile fixed slots, then ovf_cap overflow records
