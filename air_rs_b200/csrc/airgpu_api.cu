@@ -7,7 +7,6 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -81,7 +80,6 @@ struct airgpu_ctx {
     int format = AIRGPU_FMT_CS16;
     size_t max_buffer_samples = 0;
     size_t max_frames = 0;
-    unsigned max_ctas = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr, ev_sync = nullptr, evk0 = nullptr, evk1 = nullptr;
     bool ev_valid = false, evh_valid = false, evk_valid = false, sync_valid = false;
@@ -179,7 +177,6 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.n_tiles = g.n_tiles;
     p.base_offset = base;
     p.minus_one = 0xFFFFFFFFu;
-    p.max_ctas = c->max_ctas;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(d_iq) & 15u) == 0 && (g.n_tiles == g.tiles_per_seg || g.seg_len % 8 == 0)) ? 1u : 0u;
     p.scratch = c->scratch;
     p.cap = cap;
@@ -285,11 +282,6 @@ int airgpu_create(const airgpu_config *cfg, airgpu_ctx **out)
     c->format = (int)cfg->format;
     c->max_buffer_samples = cfg->max_buffer_samples ? cfg->max_buffer_samples : 262144;
     c->max_frames = cfg->max_frames ? cfg->max_frames : 8192;
-    {
-        const char *e = getenv("AIRGPU_CTAS_PER_SM");     // tuning knob; 0 = one CTA per 4 tiles (not persistent)
-        const int per_sm = e ? atoi(e) : 8;
-        c->max_ctas = (unsigned)(prop.multiProcessorCount * per_sm);
-    }
     unsigned n_slots = cfg->ring_slots ? cfg->ring_slots : 4;
 
 #define CUX(call)                                                                                 \

@@ -455,111 +455,107 @@ __global__ void __launch_bounds__(kThreads, AIRGPU_MIN_CTAS) decode_kernel(const
     // everything else follows from it.  The single-segment case (a long capture) avoids the
     // division; all tile starts are multiples of 2048 samples, so 16-byte alignment of the
     // loads is a per-launch property (p.vec_ok, computed by the host).
-    // Persistent warps: the grid is sized to fill the machine once and every warp walks the tiles
-    // with a grid-wide stride.  Warps drift apart as they go (their survivor work differs), so
-    // the FMA/LSU-heavy level phase of some warps overlaps the ALU-heavy preamble phase of others.
-    for (unsigned tile = blockIdx.x * kWarps + warp; tile < p.n_tiles; tile += gridDim.x * kWarps) {
-        unsigned seg = 0, tile_in_seg = tile;
-        if (!kSingleSegment) {
-            seg = tile / p.tiles_per_seg;
-            tile_in_seg = tile - seg * p.tiles_per_seg;
+    const unsigned tile = blockIdx.x * kWarps + warp;
+    if (tile >= p.n_tiles) return;
+    unsigned seg = 0, tile_in_seg = tile;
+    if (!kSingleSegment) {
+        seg = tile / p.tiles_per_seg;
+        tile_in_seg = tile - seg * p.tiles_per_seg;
+    }
+    const unsigned long long seg_start = kSingleSegment ? 0ull : (unsigned long long)seg * p.seg_len;
+    const unsigned long long seg_n = kSingleSegment ? p.n_samples : min(p.seg_len, p.n_samples - seg_start);
+    const unsigned long long wpos = (unsigned long long)tile_in_seg * kWarpTile;
+    const unsigned long long rem = seg_n > wpos ? seg_n - wpos : 0ull;
+    const int wcands = rem > (unsigned long long)kFrameSamples
+                           ? (int)min((unsigned long long)kWarpTile, rem - kFrameSamples) : 0;
+    if (wcands == 0) {
+        if (lane == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
+        return;
+    }
+    uint16_t *lv = s_lvl[warp];
+    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
+    Sink sink;
+    sink.slots = scratch + (unsigned long long)tile * (kSlotsPerTile * 3);
+    sink.overflow = nullptr;
+    sink.ovf_room = 0;
+    sink.off0 = p.base_offset + seg_start + wpos;
+    sink.seq = 0;
+    sink.gate = 0;
+
+    // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
+    const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
+    if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
+        // 9 chunks per lane in three batches; the loads of batch g+1 are in flight while
+        // batch g is converted, so a warp waits for HBM once per tile, not three times
+        // chunk c = lane + 32 m is stored at padded chunk (lane + lane/8) + 36 m: both the global
+        // and the shared address are "per-lane base + compile-time offset"
+        const uint8_t *gsrc = src + lane * kChunkBytes;
+        uint4 *sdst = reinterpret_cast<uint4 *>(lv) + (lane + (lane >> 3));
+        uint4 a[3], b[3], na[3], nb[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            a[j] = ldg_stream(gsrc + 32 * j * kChunkBytes);
+            if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(gsrc + 32 * j * kChunkBytes + 16);
         }
-        const unsigned long long seg_start = kSingleSegment ? 0ull : (unsigned long long)seg * p.seg_len;
-        const unsigned long long seg_n = kSingleSegment ? p.n_samples : min(p.seg_len, p.n_samples - seg_start);
-        const unsigned long long wpos = (unsigned long long)tile_in_seg * kWarpTile;
-        const unsigned long long rem = seg_n > wpos ? seg_n - wpos : 0ull;
-        const int wcands = rem > (unsigned long long)kFrameSamples
-                               ? (int)min((unsigned long long)kWarpTile, rem - kFrameSamples) : 0;
-        if (wcands == 0) {
-            if (lane == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
-            continue;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            if (g < 2) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int c = lane + 32 * (3 * (g + 1) + j);
+                    na[j] = ldg_stream(src + c * kChunkBytes);
+                    if (FMT == AIRGPU_FMT_CS16) nb[j] = ldg_stream(src + c * kChunkBytes + 16);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int c = lane + 32 * (3 * g + j);
+                *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j], p.minus_one);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                a[j] = na[j];
+                b[j] = nb[j];
+            }
         }
-        uint16_t *lv = s_lvl[warp];
-        unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
-        Sink sink;
-        sink.slots = scratch + (unsigned long long)tile * (kSlotsPerTile * 3);
-        sink.overflow = nullptr;
-        sink.ovf_room = 0;
-        sink.off0 = p.base_offset + seg_start + wpos;
+    } else {
+        // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
+        const long long avail = (long long)rem * BPS;   // bytes to the end of the segment
+        const int need = min(kWarpChunks, (wcands + kFrameSamples + 7) / 8);
+#pragma unroll 1
+        for (int c = lane; c < kWarpChunks; c += 32) {
+            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+            if (c < need) {
+                a = load16_guarded(src, (long long)c * kChunkBytes, avail);
+                if (FMT == AIRGPU_FMT_CS16) b = load16_guarded(src, (long long)c * kChunkBytes + 16, avail);
+            }
+            *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b, p.minus_one);
+        }
+    }
+    __syncwarp();
+
+    // ---- phase 2+3: gate, slice, CRC; frames go straight to the tile's scratch slots ----
+    scan_warp_range<FMT>(lv, s_hits[warp], wcands, lane, sink);
+    const uint32_t nvalid = sink.seq;
+
+    // ---- phase 4: publish the count (no atomic with a return value on the common path) ----
+    unsigned long long ovf_base = 0;
+    if (lane == 0) {
+        if (nvalid) atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)nvalid);            // RED
+        if (sink.gate) atomicAdd(&p.group_gate[tile / kGroupTiles], (unsigned long long)sink.gate);    // RED
+        if (nvalid > (uint32_t)kSlotsPerTile)
+            ovf_base = atomicAdd(p.ovf_counter, (unsigned long long)(nvalid - kSlotsPerTile));
+        p.tile_tab[tile] = make_uint2((unsigned)min(ovf_base, 0xFFFFFFFFull), nvalid);
+    }
+    if (nvalid > (uint32_t)kSlotsPerTile) {
+        // rare (degenerate input): second pass over the range writes frames kSlotsPerTile.. to
+        // the overflow area, which starts after all the fixed slots
+        ovf_base = __shfl_sync(kFull, ovf_base, 0);
+        sink.overflow = scratch + ((unsigned long long)p.n_tiles * kSlotsPerTile + ovf_base) * 3;
+        sink.ovf_room = p.ovf_cap > ovf_base ? p.ovf_cap - ovf_base : 0ull;
         sink.seq = 0;
         sink.gate = 0;
-
-        // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
-        const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
-        if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
-            // 9 chunks per lane in three batches; the loads of batch g+1 are in flight while
-            // batch g is converted, so a warp waits for HBM once per tile, not three times
-            // chunk c = lane + 32 m is stored at padded chunk (lane + lane/8) + 36 m: both the global
-            // and the shared address are "per-lane base + compile-time offset"
-            const uint8_t *gsrc = src + lane * kChunkBytes;
-            uint4 *sdst = reinterpret_cast<uint4 *>(lv) + (lane + (lane >> 3));
-            uint4 a[3], b[3], na[3], nb[3];
-    #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                a[j] = ldg_stream(gsrc + 32 * j * kChunkBytes);
-                if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(gsrc + 32 * j * kChunkBytes + 16);
-            }
-    #pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                if (g < 2) {
-    #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const int c = lane + 32 * (3 * (g + 1) + j);
-                        na[j] = ldg_stream(src + c * kChunkBytes);
-                        if (FMT == AIRGPU_FMT_CS16) nb[j] = ldg_stream(src + c * kChunkBytes + 16);
-                    }
-                }
-    #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int c = lane + 32 * (3 * g + j);
-                    *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j], p.minus_one);
-                }
-    #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    a[j] = na[j];
-                    b[j] = nb[j];
-                }
-            }
-        } else {
-            // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
-            const long long avail = (long long)rem * BPS;   // bytes to the end of the segment
-            const int need = min(kWarpChunks, (wcands + kFrameSamples + 7) / 8);
-    #pragma unroll 1
-            for (int c = lane; c < kWarpChunks; c += 32) {
-                uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-                if (c < need) {
-                    a = load16_guarded(src, (long long)c * kChunkBytes, avail);
-                    if (FMT == AIRGPU_FMT_CS16) b = load16_guarded(src, (long long)c * kChunkBytes + 16, avail);
-                }
-                *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b, p.minus_one);
-            }
-        }
-        __syncwarp();
-
-        // ---- phase 2+3: gate, slice, CRC; frames go straight to the tile's scratch slots ----
         scan_warp_range<FMT>(lv, s_hits[warp], wcands, lane, sink);
-        const uint32_t nvalid = sink.seq;
-
-        // ---- phase 4: publish the count (no atomic with a return value on the common path) ----
-        unsigned long long ovf_base = 0;
-        if (lane == 0) {
-            if (nvalid) atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)nvalid);            // RED
-            if (sink.gate) atomicAdd(&p.group_gate[tile / kGroupTiles], (unsigned long long)sink.gate);    // RED
-            if (nvalid > (uint32_t)kSlotsPerTile)
-                ovf_base = atomicAdd(p.ovf_counter, (unsigned long long)(nvalid - kSlotsPerTile));
-            p.tile_tab[tile] = make_uint2((unsigned)min(ovf_base, 0xFFFFFFFFull), nvalid);
-        }
-        if (nvalid > (uint32_t)kSlotsPerTile) {
-            // rare (degenerate input): second pass over the range writes frames kSlotsPerTile.. to
-            // the overflow area, which starts after all the fixed slots
-            ovf_base = __shfl_sync(kFull, ovf_base, 0);
-            sink.overflow = scratch + ((unsigned long long)p.n_tiles * kSlotsPerTile + ovf_base) * 3;
-            sink.ovf_room = p.ovf_cap > ovf_base ? p.ovf_cap - ovf_base : 0ull;
-            sink.seq = 0;
-            sink.gate = 0;
-            scan_warp_range<FMT>(lv, s_hits[warp], wcands, lane, sink);
-        }
-        __syncwarp();     // the next tile reuses this warp's shared-memory slice
     }
 }
 
@@ -688,8 +684,7 @@ __global__ void levels_cs16_kernel(const uint32_t *iq, unsigned long long n, uin
 cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream)
 {
     if (p.n_tiles == 0) return cudaSuccess;
-    unsigned grid = (p.n_tiles + kWarps - 1) / kWarps;
-    if (p.max_ctas && grid > p.max_ctas) grid = p.max_ctas;   // persistent: one resident wave
+    const unsigned grid = (p.n_tiles + kWarps - 1) / kWarps;
     const bool single = p.tiles_per_seg >= p.n_tiles;     // one segment: no per-tile division
     if (format == AIRGPU_FMT_U8) {
         if (single) decode_kernel<AIRGPU_FMT_U8, true><<<grid, kThreads, 0, stream>>>(p);

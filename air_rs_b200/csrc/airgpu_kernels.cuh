@@ -34,7 +34,6 @@ struct DecodeParams {
     unsigned int tiles_per_seg;
     unsigned int n_tiles;           // n_segments * tiles_per_seg
     unsigned int minus_one;         // 0xFFFFFFFF (see levels_u8_pair)
-    unsigned int max_ctas;          // grid cap for the persistent decode kernel (SMs * resident CTAs)
     unsigned int vec_ok;            // every warp slice starts 16-byte aligned (base aligned, seg_len % 8 == 0)
     unsigned long long base_offset; // added to every frame offset
     airgpu_frame *scratch;          // n_tiles * kSlotsPerTile fixed slots, then ovf_cap overflow records
