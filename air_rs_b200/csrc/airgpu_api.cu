@@ -577,6 +577,39 @@ int airgpu_collect(airgpu_ctx *c, uint64_t ticket, airgpu_frame *out, size_t cap
 }
 
 // ---------------------------------------------------------------------------
+// N1: frame field decode
+// ---------------------------------------------------------------------------
+int airgpu_decode_fields(airgpu_ctx *c, const airgpu_frame *d_frames, size_t n_frames, airgpu_fields *d_out,
+                         void *stream)
+{
+    if (!c) return fail(AIRGPU_ERR_INVALID, "ctx is NULL");
+    if (n_frames && (!d_frames || !d_out)) return fail(AIRGPU_ERR_INVALID, "NULL device pointer");
+    CU(cudaSetDevice(c->device));
+    CU(launch_decode_fields(d_frames, n_frames, d_out, stream ? (cudaStream_t)stream : c->compute));
+    return AIRGPU_OK;
+}
+
+int airgpu_decode_fields_host(airgpu_ctx *c, const airgpu_frame *frames, size_t n_frames, airgpu_fields *out)
+{
+    if (!c) return fail(AIRGPU_ERR_INVALID, "ctx is NULL");
+    if (n_frames == 0) return AIRGPU_OK;
+    if (!frames || !out) return fail(AIRGPU_ERR_INVALID, "NULL buffer");
+    CU(cudaSetDevice(c->device));
+    airgpu_frame *d_in = nullptr;
+    airgpu_fields *d_out = nullptr;
+    CU(cudaMalloc(&d_in, n_frames * sizeof(airgpu_frame)));
+    cudaError_t e = cudaMalloc(&d_out, n_frames * sizeof(airgpu_fields));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, frames, n_frames * sizeof(airgpu_frame), cudaMemcpyHostToDevice, c->compute);
+    if (e == cudaSuccess) e = launch_decode_fields(d_in, n_frames, d_out, c->compute);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n_frames * sizeof(airgpu_fields), cudaMemcpyDeviceToHost, c->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute);
+    cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    CU(e);
+    return AIRGPU_OK;
+}
+
+// ---------------------------------------------------------------------------
 // diagnostics used by the parity tests (device arithmetic only)
 // ---------------------------------------------------------------------------
 int airgpu_dbg_levels_u8(airgpu_ctx *c, uint16_t *out65536)

@@ -667,6 +667,50 @@ gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const un
     }
 }
 
+// ---- N1: frame fields -------------------------------------------------------------
+// One thread per frame: three 8-byte loads, integer bit twiddling, two 16-byte stores.
+// HBM bound by construction (24 B in, 32 B out per frame).
+__global__ void __launch_bounds__(256) fields_kernel(const unsigned long long *frames, unsigned long long n,
+                                                     uint4 *out)
+{
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned long long w0 = frames[3 * k], w1 = frames[3 * k + 1];
+    unsigned char b[14];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (unsigned char)(w0 >> (8 * i));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) b[8 + i] = (unsigned char)(w1 >> (8 * i));
+    const unsigned char *me = b + 4;                       // packet[4..11]
+    const uint32_t icao = ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    const uint32_t df = b[0] >> 3, ca = b[0] & 5u, tc = me[0] >> 3;
+    uint32_t kind = 0, alt = 0, lat = 0, lon = 0, flags = 0;
+    unsigned long long cs = 0;
+    if (tc >= 1 && tc <= 4) {                              // msgs.rs:208-213, 171-187
+        kind = 1;
+        unsigned long long acc = 0;
+#pragma unroll
+        for (int i = 1; i < 7; ++i) acc = (acc << 8) | me[i];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t v = (uint32_t)(acc >> (42 - 6 * c)) & 0x3Fu;
+            // msgs.rs:164-169 CHAR_CONVERT: 1-26 letters, 32 '_', 48-57 digits, else '#'
+            const uint32_t ch = (v >= 1 && v <= 26) ? ('A' + v - 1) : (v == 32) ? '_' : (v >= 48 && v <= 57) ? v : '#';
+            cs |= (unsigned long long)ch << (8 * c);
+        }
+    } else if (tc >= 9 && tc <= 18) {                      // msgs.rs:121-125, 69-102
+        kind = 2;
+        int a = (int)((((uint32_t)me[1] & 0xFEu) >> 1) << 4) | (int)(((uint32_t)me[2] & 0xF0u) >> 4);
+        a = a * ((me[1] & 1u) ? 25 : 100) - 1000;
+        alt = (uint32_t)a;
+        lat = (((uint32_t)me[2] & 3u) << 15) | ((uint32_t)me[3] << 7) | (((uint32_t)me[4] & 0xFEu) >> 1);
+        lon = (((uint32_t)me[4] & 1u) << 16) | ((uint32_t)me[5] << 8) | me[6];
+        flags = ((me[0] & 6u) >> 1) | ((me[0] & 1u) << 8) | (((me[2] & 8u) >> 3) << 16) | (((me[2] & 4u) >> 2) << 24);
+    }
+    out[2 * k] = make_uint4(icao, df | (ca << 8) | (tc << 16) | (kind << 24), alt, lat);
+    out[2 * k + 1] = make_uint4(lon, flags, (uint32_t)cs, (uint32_t)(cs >> 32));
+}
+
 __global__ void levels_u8_kernel(uint16_t *out, uint32_t minus_one)
 {
     unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = I | Q << 8
@@ -708,6 +752,15 @@ cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned l
     gather_kernel<<<n_groups, kGroupTiles, 0, stream>>>(reinterpret_cast<const unsigned long long *>(p.scratch),
                                                         p.tile_tab, p.group_base, p.n_tiles,
                                                         reinterpret_cast<unsigned long long *>(out), p.cap, p.ovf_cap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_fields(const airgpu_frame *frames, unsigned long long n, airgpu_fields *out, cudaStream_t stream)
+{
+    static_assert(sizeof(airgpu_fields) == 32, "airgpu_fields layout");
+    if (n == 0) return cudaSuccess;
+    fields_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const unsigned long long *>(frames), n,
+                                                                    reinterpret_cast<uint4 *>(out));
     return cudaGetLastError();
 }
 

@@ -55,6 +55,9 @@ cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream
 cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned long long *d_total,
                             cudaStream_t stream);
 
+// N1: per-frame field decode (packet.rs:25-49, msgs.rs:69-102, 171-201).
+cudaError_t launch_decode_fields(const airgpu_frame *frames, unsigned long long n, airgpu_fields *out, cudaStream_t stream);
+
 // Exhaustive self-check helper used by the tests: level (inverted magnitude proxy)
 // the kernel computes for every U8 (I, Q) pair / for a list of CS16 samples.
 cudaError_t launch_levels_u8(uint16_t *out65536, cudaStream_t stream);

@@ -144,6 +144,17 @@ class AdsbDecoder:
         n = min(count, out.shape[0])
         return out[:n].cpu().numpy().view(FRAME_DTYPE).reshape(-1).copy()
 
+    # -- N1: frame fields ------------------------------------------------------
+    def decode_fields(self, frames: np.ndarray) -> np.ndarray:
+        """Per-frame derived fields (AdsbPacket::new on the device); host arrays in and out."""
+        fr = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        out = np.zeros(fr.size, dtype=native.FIELDS_DTYPE)
+        native.check(self._lib.airgpu_decode_fields_host(self._h, fr.ctypes.data, fr.size, out.ctypes.data))
+        return out
+
+    def decode_fields_device(self, d_frames: int, n_frames: int, d_out: int, stream: int = 0) -> None:
+        native.check(self._lib.airgpu_decode_fields(self._h, d_frames, n_frames, d_out, stream or None))
+
     def stats(self) -> dict:
         st = native.Stats()
         native.check(self._lib.airgpu_get_stats(self._h, C.byref(st)))

@@ -22,6 +22,16 @@ FRAME_DTYPE = np.dtype(
 )
 assert FRAME_DTYPE.itemsize == 24
 
+# airgpu_fields, 32 bytes
+FIELDS_DTYPE = np.dtype(
+    [("icao", np.uint32), ("downlink_format", np.uint8), ("capability", np.uint8), ("msg_type", np.uint8),
+     ("kind", np.uint8), ("altitude", np.int32), ("cpr_latitude", np.uint32), ("cpr_longitude", np.uint32),
+     ("surveillance_status", np.uint8), ("nic_supplement", np.uint8), ("cpr_time", np.uint8), ("cpr_odd", np.uint8),
+     ("callsign", "S8")],
+    align=True,
+)
+assert FIELDS_DTYPE.itemsize == 32
+
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_OVERFLOW, ERR_BUSY, ERR_TICKET = 0, -1, -2, -3, -4, -5, -6, -7
 
 
@@ -70,6 +80,8 @@ SYMBOLS = {
     "airgpu_decode_device": (C.c_int, [_vp, _vp, _sz, _sz, _u64, _vp, _sz, _vp, _vp]),
     "airgpu_sync_count": (C.c_int, [_vp, C.POINTER(_u64)]),
     "airgpu_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "airgpu_decode_fields": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "airgpu_decode_fields_host": (C.c_int, [_vp, _vp, _sz, _vp]),
     "airgpu_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "airgpu_host_free": (C.c_int, [_vp]),
     "airgpu_dbg_levels_u8": (C.c_int, [_vp, _vp]),

@@ -145,6 +145,34 @@ int airgpu_sync_count(airgpu_ctx *ctx, uint64_t *n_frames);
 
 int airgpu_get_stats(airgpu_ctx *ctx, airgpu_stats *out);
 
+/* ---- next row N1: frame field decode on the device ---------------------------- *
+ * What AdsbPacket::new derives from the 14 bytes (src/adsb/packet.rs:25-49) and the
+ * two message decoders it calls (src/adsb/msgs.rs:69-102 AircraftPosition::new,
+ * :171-201 AircraftID::new), one record per frame, so that an exchange of decoded
+ * records can replace an exchange of raw frames.  Quirks kept: capability = b0 & 5. */
+typedef struct airgpu_fields {
+    uint32_t icao;                 /* packet.rs:28                                        */
+    uint8_t  downlink_format;      /* b0 >> 3                                             */
+    uint8_t  capability;           /* b0 & 5 (sic, packet.rs:27)                          */
+    uint8_t  msg_type;             /* b4 >> 3 (type code)                                 */
+    uint8_t  kind;                 /* 0 Uknown, 1 AircraftID (TC 1-4), 2 AircraftPosition (TC 9-18) */
+    int32_t  altitude;             /* feet, msgs.rs:71-75 (position only, else 0)         */
+    uint32_t cpr_latitude;         /* 17 bits, msgs.rs:84-86                              */
+    uint32_t cpr_longitude;        /* 17 bits, msgs.rs:87-89                              */
+    uint8_t  surveillance_status;  /* msgs.rs:78                                          */
+    uint8_t  nic_supplement;       /* msgs.rs:79                                          */
+    uint8_t  cpr_time;             /* msgs.rs:80                                          */
+    uint8_t  cpr_odd;              /* msgs.rs:81-82: 1 = CprFormat::Odd                   */
+    char     callsign[8];          /* msgs.rs:164-187, not NUL terminated (ID only, else zeros) */
+} airgpu_fields;                   /* 32 bytes */
+
+/* d_frames / d_out are device pointers; stream is a cudaStream_t (NULL = compute stream). */
+int airgpu_decode_fields(airgpu_ctx *ctx, const airgpu_frame *d_frames, size_t n_frames,
+                         airgpu_fields *d_out, void *stream);
+/* Convenience for host arrays (copies in, decodes, copies out, synchronises). */
+int airgpu_decode_fields_host(airgpu_ctx *ctx, const airgpu_frame *frames, size_t n_frames,
+                              airgpu_fields *out);
+
 /* Page-locked host buffers ("pinned host ring buffers"): a receive thread that
  * fills buffers from airgpu_host_alloc lets airgpu_decode copy asynchronously
  * straight from them.  Replaces the plain Vec allocations at src/adsb.rs:60,64,78. */

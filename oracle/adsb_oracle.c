@@ -528,3 +528,66 @@ size_t oracle_decode_fast(const void *iq, size_t n_samples, int format,
     return decode_split(iq, n_samples, format, segment_samples, base, out, cap, gate_passes,
                         n_threads, 0);
 }
+
+/* ========================================================================= */
+/* N1: AdsbPacket::new field derivation (literal restatement)                */
+/* ========================================================================= */
+
+/* msgs.rs:141-162 */
+static size_t to_6bit_chunks(const uint8_t *input, size_t n, uint8_t *out)
+{
+    uint32_t acc = 0;
+    int bits = 0;
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i) {
+        acc = (acc << 8) | input[i];
+        bits += 8;
+        while (bits >= 6) {
+            bits -= 6;
+            out[k++] = (uint8_t)((acc >> bits) & 0x3F);
+        }
+    }
+    if (bits > 0)
+        out[k++] = (uint8_t)((acc << (6 - bits)) & 0x3F);
+    return k;
+}
+
+/* msgs.rs:164-169 */
+static const char CHAR_CONVERT[65] =
+    "#ABCDEFGHIJKLMNOPQRSTUVWXYZ#####_###############0123456789######";
+
+void oracle_packet_fields(const uint8_t packet[14], oracle_fields *o)
+{
+    memset(o, 0, sizeof *o);
+    o->downlink_format = packet[0] >> 3;                                  /* packet.rs:26 */
+    o->capability = packet[0] & 5;                                        /* packet.rs:27 (sic) */
+    o->icao = ((uint32_t)packet[1] << 16) | ((uint32_t)packet[2] << 8) | packet[3];
+    o->msg_type = packet[4] >> 3;                                         /* packet.rs:29 */
+    const uint8_t *msg = packet + 4;                                      /* packet[4..4+7] */
+    if (1 <= o->msg_type && o->msg_type <= 4) {                           /* msgs.rs:208-213 */
+        uint8_t six[16];
+        size_t n = to_6bit_chunks(msg + 1, 6, six);                       /* msgs.rs:173 */
+        o->kind = 1;
+        for (size_t k = 0; k < n && k < 8; ++k)
+            o->callsign[k] = six[k] < 64 ? CHAR_CONVERT[six[k]] : '?';
+    } else if (9 <= o->msg_type && o->msg_type <= 18) {                   /* msgs.rs:121-125 */
+        o->kind = 2;
+        int alt_mode_25 = (msg[1] & (1 << 0)) == 1;                       /* msgs.rs:70 */
+        int32_t altitude = ((int32_t)((msg[1] & 0xFE) >> 1) << 4) | ((int32_t)(msg[2] & 0xF0) >> 4);
+        altitude *= alt_mode_25 ? 25 : 100;
+        altitude -= 1000;
+        o->altitude = altitude;
+        o->surveillance_status = (msg[0] & 0x06) >> 1;
+        o->nic_supplement = msg[0] & 0x01;
+        o->cpr_time = (msg[2] & 0x08) >> 3;
+        o->cpr_odd = ((msg[2] & 0x04) >> 2) == 1;
+        o->cpr_latitude = ((uint32_t)(msg[2] & 0x03) << 15) | ((uint32_t)msg[3] << 7) | (((uint32_t)msg[4] & 0xFE) >> 1);
+        o->cpr_longitude = ((uint32_t)(msg[4] & 0x01) << 16) | ((uint32_t)msg[5] << 8) | (uint32_t)msg[6];
+    }
+}
+
+void oracle_frames_fields(const oracle_frame *frames, size_t n, oracle_fields *out)
+{
+    for (size_t k = 0; k < n; ++k)
+        oracle_packet_fields(frames[k].bytes, &out[k]);
+}

@@ -111,6 +111,22 @@ size_t oracle_decode_literal_mt(const void *iq, size_t n_samples, int format,
                                 oracle_frame *out, size_t cap, uint64_t *gate_passes,
                                 int n_threads);
 
+/* ---- next row N1: what AdsbPacket::new derives from the 14 bytes ------------------ *
+ * src/adsb/packet.rs:25-49, src/adsb/msgs.rs:69-102 (AircraftPosition::new),
+ * :141-162 (to_6bit_chunks), :164-187 (CHAR_CONVERT, AircraftID::new).  Same 32-byte layout as
+ * airgpu_fields.  Pinned by the reference's unit tests msgs.rs:225-321 (tests/test_fields.py). */
+typedef struct {
+    uint32_t icao;
+    uint8_t  downlink_format, capability, msg_type, kind;   /* kind: 0 Uknown, 1 AircraftID, 2 AircraftPosition */
+    int32_t  altitude;
+    uint32_t cpr_latitude, cpr_longitude;
+    uint8_t  surveillance_status, nic_supplement, cpr_time, cpr_odd;
+    char     callsign[8];
+} oracle_fields;
+
+void oracle_packet_fields(const uint8_t packet[14], oracle_fields *out);
+void oracle_frames_fields(const oracle_frame *frames, size_t n, oracle_fields *out);
+
 /* 88 single-bit syndromes T[p] = crc(e_p) used by the fast path (for tests). */
 void oracle_syndrome_table(uint32_t table[88]);
 

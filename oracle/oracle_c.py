@@ -24,6 +24,15 @@ FRAME_DTYPE = np.dtype(
 )
 assert FRAME_DTYPE.itemsize == 24
 
+FIELDS_DTYPE = np.dtype(
+    [("icao", np.uint32), ("downlink_format", np.uint8), ("capability", np.uint8), ("msg_type", np.uint8),
+     ("kind", np.uint8), ("altitude", np.int32), ("cpr_latitude", np.uint32), ("cpr_longitude", np.uint32),
+     ("surveillance_status", np.uint8), ("nic_supplement", np.uint8), ("cpr_time", np.uint8), ("cpr_odd", np.uint8),
+     ("callsign", "S8")],
+    align=True,
+)
+assert FIELDS_DTYPE.itemsize == 32
+
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with gcc (a few hundred ms). Safe to call repeatedly."""
@@ -69,6 +78,8 @@ def lib() -> C.CDLL:
         L.oracle_decode_literal_mt.restype = C.c_size_t
         L.oracle_decode_fast.argtypes = common + [C.c_int]
         L.oracle_decode_fast.restype = C.c_size_t
+        L.oracle_frames_fields.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.oracle_frames_fields.restype = None
         L.oracle_syndrome_table.argtypes = [u32p]
         L.oracle_syndrome_table.restype = None
         del u8p, u16p
@@ -172,3 +183,17 @@ def syndrome_table() -> np.ndarray:
     t = np.zeros(88, dtype=np.uint32)
     lib().oracle_syndrome_table(t.ctypes.data_as(C.POINTER(C.c_uint32)))
     return t
+
+
+def frames_fields(frames: np.ndarray) -> np.ndarray:
+    """AdsbPacket::new field derivation for every frame record (N1 oracle)."""
+    fr = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+    out = np.zeros(fr.size, dtype=FIELDS_DTYPE)
+    lib().oracle_frames_fields(fr.ctypes.data, fr.size, out.ctypes.data)
+    return out
+
+
+def packet_fields(packet: bytes):
+    fr = np.zeros(1, dtype=FRAME_DTYPE)
+    fr["bytes"][0] = np.frombuffer(bytes(packet), dtype=np.uint8)
+    return frames_fields(fr)[0]
