@@ -70,6 +70,23 @@ def build_host(force: bool = False) -> Path:
     return HOST_BIN
 
 
+HOST_LIB = LIBDIR / "libadsb_host.so"
+
+
+def build_host_lib(force: bool = False) -> Path:
+    """Compile the CUDA-free host mirror of the tracker / CPR / JSON summary (csrc/host) with its C shims."""
+    srcs = [CSRC / "host" / "adsb_host_c.cpp", CSRC / "host" / "adsb_track.hpp", CSRC / "host" / "adsb_host.hpp"]
+    LIBDIR.mkdir(exist_ok=True)
+    stale = (not HOST_LIB.exists()) or HOST_LIB.stat().st_mtime < max(f.stat().st_mtime for f in srcs)
+    if force or stale:
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", str(HOST_LIB), str(srcs[0])]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
     print(build_host(force=True))
+    print(build_host_lib(force=True))

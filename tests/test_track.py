@@ -1,0 +1,106 @@
+"""CPU: the C++ host mirror of the reference's post-decode logic (SURVEY 8(f) rows N2 and N4:
+csrc/host/adsb_track.hpp) against the reference's own unit tests, through C shims and ctypes.
+  cpr.rs:152-188       test_latitude_calculation, test_zone_calcuation, test_longitude_calculation
+  cpr.rs:190-207       test_identify_issue_with_latitude
+  aircraft.rs:177-262  id, altitude, the two even/odd position pairs
+  aircraft.rs:14-23    AircraftSummary wire format (camelCase; bindings/AircraftSummary.ts)"""
+import ctypes as C
+import json
+
+import pytest
+
+from air_rs_b200 import build
+
+
+@pytest.fixture(scope="module")
+def host():
+    lib = C.CDLL(str(build.build_host_lib()))
+    lib.adsb_host_calc_num_zones.argtypes = [C.c_double]
+    lib.adsb_host_calc_num_zones.restype = C.c_uint
+    lib.adsb_host_calculate_latitude.argtypes = [C.c_uint, C.c_uint, C.c_int, C.POINTER(C.c_double)]
+    lib.adsb_host_calculate_longitude.argtypes = [C.c_uint, C.c_uint, C.c_double, C.c_int]
+    lib.adsb_host_calculate_longitude.restype = C.c_double
+    lib.adsb_host_tracker_new.restype = C.c_void_p
+    lib.adsb_host_tracker_free.argtypes = [C.c_void_p]
+    lib.adsb_host_tracker_update.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_char_p, C.c_size_t]
+    lib.adsb_host_tracker_update.restype = C.c_size_t
+    return lib
+
+
+def _lat(host, e, o, first_is_odd):
+    out = (C.c_double * 3)()
+    host.adsb_host_calculate_latitude(e, o, int(first_is_odd), out)
+    return tuple(out)
+
+
+def test_cpr_zones(host):
+    """cpr.rs:163-177"""
+    for lat, nl in ((0.0, 59), (87.0, 2), (-87.0, 2), (90.0, 1), (-90.0, 1), (10.0, 59), (52.25720214843750, 36)):
+        assert host.adsb_host_calc_num_zones(lat) == nl
+
+
+def test_cpr_latitude_longitude(host):
+    """cpr.rs:152-160, 179-188.
+
+    The upstream test_longitude_calculation expects 3.829498291015625 (= 10 * odd_lon) for first = Odd, but
+    the CODE at cpr.rs:114-121 uses the EVEN longitude when the newest message is even (first = Odd):
+    divisions * (m % nz + lon_cpr_e) = 10 * 51372 / 131072 = 3.91937255859375 -- the textbook answer for
+    this classic pair.  Like demod.rs:322-335 that upstream expectation is stale; the code is the spec
+    (the second pair below reproduces the values upstream printed from a real run to 1e-14)."""
+    assert abs(_lat(host, 93000, 74158, True)[0] - 52.25720) < 1e-4
+    lon = host.adsb_host_calculate_longitude(51372, 50194, 52.25720214843750, 1)
+    assert abs(lon - 3.91937255859375) < 1e-12
+    assert abs(lon - 3.829498291015625) > 0.08            # documents the stale upstream expectation
+    lon = host.adsb_host_calculate_longitude(51372, 50194, 52.25720214843750, 0)   # newest is odd
+    assert abs(lon - 360.0 / 35 * (50194 / 131072)) < 1e-12
+
+
+def test_cpr_zone_consistency_case(host):
+    """cpr.rs:190-207"""
+    _, even_lat, odd_lat = _lat(host, 23868, 38688, True)
+    assert host.adsb_host_calc_num_zones(even_lat) == host.adsb_host_calc_num_zones(odd_lat)
+
+
+def _update(host, t, hexframe, now):
+    buf = C.create_string_buffer(512)
+    n = host.adsb_host_tracker_update(t, bytes.fromhex(hexframe), now, buf, 512)
+    assert n > 0
+    return json.loads(buf.value.decode()), buf.value.decode()
+
+
+def test_tracker_and_summary_json(host):
+    t = host.adsb_host_tracker_new()
+    try:
+        s, raw = _update(host, t, "8d7c6b3020293532d70820fc8090", 1000.0)          # aircraft.rs:184-191
+        assert s == {"icao": 0x7C6B30, "callsign": "JST250__", "altitude": 0, "geoPosition": None, "lastContact": 1000}
+        assert raw.startswith('{"icao":8154928,"callsign":"JST250__","altitude":0,"geoPosition":null,"lastContact":')
+        s, _ = _update(host, t, "8d7c6b30581304f388bb4455896f", 1001.0)            # aircraft.rs:193-199
+        assert s["altitude"] == 2600 and s["callsign"] == "JST250__"
+        _update(host, t, "8D40621D58C386435CC412692AD6", 1002.0)                  # aircraft.rs:201-213
+        s, raw = _update(host, t, "8D40621D58C382D690C8AC2863A7", 1003.5)
+        assert s["icao"] == 0x40621D and s["altitude"] == 38000 and s["lastContact"] == 1003
+        assert abs(s["geoPosition"]["latitude"] - 52.25720) < 1e-4
+        assert abs(s["geoPosition"]["longitude"] - 3.91937255859375) < 1e-12   # upstream's 3.8295 is stale, see above
+        assert '"geoPosition":{"latitude":52.2572021484375,"longitude":3.91937255859375}' in raw
+        assert list(s.keys()) == ["icao", "callsign", "altitude", "geoPosition", "lastContact"]
+        assert list(s["geoPosition"].keys()) == ["latitude", "longitude"]
+        _update(host, t, "8d7c6b30580d107903b3cabf62ab", 1004.0)                  # aircraft.rs:215-262
+        s, _ = _update(host, t, "8d7c6b30580d24eeaebb2dfea5bb", 1005.0)
+        assert s["altitude"] == 1450
+        assert abs(s["geoPosition"]["latitude"] - -41.28964698920816) < 1e-12   # upstream's printed run, to the last digit
+        assert abs(s["geoPosition"]["longitude"] - 174.80927207253197) < 1e-12
+    finally:
+        host.adsb_host_tracker_free(t)
+
+
+def test_pairing_window_is_ten_seconds(host):
+    """aircraft.rs:66-68, 85-87: an even/odd pair more than 10 s apart gives no position"""
+    t = host.adsb_host_tracker_new()
+    try:
+        _update(host, t, "8D40621D58C386435CC412692AD6", 0.0)
+        s, _ = _update(host, t, "8D40621D58C382D690C8AC2863A7", 10.5)
+        assert s["geoPosition"] is None and s["altitude"] == 38000
+        s, _ = _update(host, t, "8D40621D58C386435CC412692AD6", 12.0)             # odd again, 1.5 s after the even
+        assert s["geoPosition"] is not None
+    finally:
+        host.adsb_host_tracker_free(t)
