@@ -52,7 +52,8 @@ def test_cpr_latitude_longitude(host):
     assert abs(lon - 3.91937255859375) < 1e-12
     assert abs(lon - 3.829498291015625) > 0.08            # documents the stale upstream expectation
     lon = host.adsb_host_calculate_longitude(51372, 50194, 52.25720214843750, 0)   # newest is odd
-    assert abs(lon - 360.0 / 35 * (50194 / 131072)) < 1e-12
+    nz = host.adsb_host_calc_num_zones(52.25720214843750 - 1.0)       # cpr.rs:103: NL(latitude - 1.0), as written upstream
+    assert abs(lon - 360.0 / nz * (50194 / 131072)) < 1e-12
 
 
 def test_cpr_zone_consistency_case(host):
@@ -73,7 +74,7 @@ def test_tracker_and_summary_json(host):
     try:
         s, raw = _update(host, t, "8d7c6b3020293532d70820fc8090", 1000.0)          # aircraft.rs:184-191
         assert s == {"icao": 0x7C6B30, "callsign": "JST250__", "altitude": 0, "geoPosition": None, "lastContact": 1000}
-        assert raw.startswith('{"icao":8154928,"callsign":"JST250__","altitude":0,"geoPosition":null,"lastContact":')
+        assert raw == '{"icao":8153904,"callsign":"JST250__","altitude":0,"geoPosition":null,"lastContact":1000}'
         s, _ = _update(host, t, "8d7c6b30581304f388bb4455896f", 1001.0)            # aircraft.rs:193-199
         assert s["altitude"] == 2600 and s["callsign"] == "JST250__"
         _update(host, t, "8D40621D58C386435CC412692AD6", 1002.0)                  # aircraft.rs:201-213
