@@ -9,18 +9,19 @@
 #include <cstring>
 #include <thread>
 
-#include "adsb_host.hpp"
+#include "adsb_track.hpp"
 
 using namespace adsb_host;
 
 int main(int argc, char **argv)
 {
     if (argc < 2) {
-        std::fprintf(stderr, "usage: %s <capture.c16> [chunk_samples=20000] [device=0]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s <capture.c16> [chunk_samples=20000] [device=0] [stream|json]\n", argv[0]);
         return 2;
     }
     const size_t chunk = argc > 2 ? std::strtoull(argv[2], nullptr, 10) : 20000;
     const int device = argc > 3 ? std::atoi(argv[3]) : 0;
+    const bool json_mode = argc > 4 && std::strcmp(argv[4], "json") == 0;   // what the web thread broadcasts
 
     airgpu_config cfg;
     std::memset(&cfg, 0, sizeof cfg);
@@ -51,7 +52,15 @@ int main(int argc, char **argv)
     std::thread stream_thread([&] { playback_thread(raw, data, chunk); });
     std::thread process_thread([&] { sent = process_sdr_data_thread(raw, msgs, ctx); });
     std::thread display_thread([&] {
+        AircraftMap aircrafts;
+        double now = 0.0;     // replay clock: one tick per packet, so the 10 s pairing window is deterministic
         while (auto p = msgs.recv()) {
+            if (json_mode) {  // web.rs:117-126: handle_aircraft_update -> get_summary -> serde_json::to_string
+                now += 0.001;
+                const Aircraft a = handle_aircraft_update(*p, aircrafts, now);
+                std::printf("Broadcasting aircraft summary: %s\n", summary_json(a).c_str());
+                continue;
+            }
             std::printf("== %s == DF %u CA %u ICAO %06X TC %u", p->hex().c_str(), p->downlink_format, p->capability,
                         p->icao, p->msg_type);
             if (p->kind == AdsbPacket::Kind::AircraftID) std::printf(" callsign %s", p->callsign.c_str());
