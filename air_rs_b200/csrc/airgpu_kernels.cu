@@ -159,16 +159,20 @@ __device__ __forceinline__ uint32_t lvl(const uint16_t *s, int i) { return s[phy
 
 // DF = 17 test on the first five data bits (demod.rs:45-54), inverted levels.
 // Levels j..j+9 are consecutive in shared memory except that one pad (8 positions) may fall
-// inside the run: two base pointers and a per-level select keep it branch free.
+// inside the run (16 % of the hits).
 __device__ __forceinline__ bool df17_ok(const uint16_t *s, int i)
 {
     const int j = i + 16;
     const uint16_t *qa = s + phys_idx(j);
-    const uint16_t *qb = qa + 8;
     const int cross = 64 - (j & 63);      // first k that lies behind the pad (>= 10: none)
     uint32_t v[10];
+    if (cross >= 10) {
 #pragma unroll
-    for (int k = 0; k < 10; ++k) v[k] = (k >= cross ? qb : qa)[k];
+        for (int k = 0; k < 10; ++k) v[k] = qa[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = qa[k + (k >= cross ? 8 : 0)];
+    }
     const uint32_t hi = max(max(max(v[0], v[3]), max(v[5], v[7])), v[8]);
     const uint32_t lo = min(min(min(v[1], v[2]), min(v[4], v[6])), v[9]);
     return hi <= lo;
@@ -234,17 +238,16 @@ __device__ __forceinline__ Cand process_candidate(const uint16_t *s, int i, int 
     return c;
 }
 
-// The three little-endian u64 words of an airgpu_frame record.
+// The three little-endian u64 words of an airgpu_frame record; lane `which` (0..2) gets its word.
+// Computed without branches: every lane forms all three and selects.
 __device__ __forceinline__ unsigned long long record_word(const Cand &c, unsigned long long offset, int which)
 {
-    if (which == 0)
-        return (unsigned long long)__byte_perm(c.w0, 0, 0x0123) |
-               ((unsigned long long)__byte_perm(c.w1, 0, 0x0123) << 32);
-    if (which == 1) {
-        uint32_t hi = ((c.w3 >> 24) & 0xFFu) | (((c.w3 >> 16) & 0xFFu) << 8) | (c.fixed << 16);
-        return (unsigned long long)__byte_perm(c.w2, 0, 0x0123) | ((unsigned long long)hi << 32);
-    }
-    return offset;
+    const unsigned long long w0 = (unsigned long long)__byte_perm(c.w0, 0, 0x0123) |
+                                  ((unsigned long long)__byte_perm(c.w1, 0, 0x0123) << 32);
+    // bytes 12, 13 of the frame, then fixed_bit, then the reserved zero byte
+    const uint32_t hi = __byte_perm(c.w3, c.fixed, 0x7423);
+    const unsigned long long w1 = (unsigned long long)__byte_perm(c.w2, 0, 0x0123) | ((unsigned long long)hi << 32);
+    return which == 0 ? w0 : (which == 1 ? w1 : offset);
 }
 
 // 3-input packed min/max: VIMNMX3.U16x2 (64 lanes/clk/SM).  Splitting them into 2-input
@@ -368,22 +371,24 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
         // hit per lane, so the DF test runs once for all of them instead of once per hit of
         // the busiest lane; survivors are then emitted in ascending offset order by repeated
         // warp-wide minimum.
-        uint32_t incl = nh;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(kFull, incl, d);
-            if (lane >= d) incl += y;
-        }
-        uint32_t pos = incl - nh;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t m = half ? pmB : pmA;
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const int o = 16 * (((b >> 2) & 1) ^ 1) + 4 * (3 - (b & 3)) + (b >> 3);
-                hitlist[pos++] = (uint16_t)(half * 1024 + lane * 32 + o);
+        // one hit per lane and round; a round is one ballot (the list order is irrelevant, the
+        // emission below orders by offset)
+        uint32_t a = pmA, b = pmB, base = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        for (;;) {
+            const bool has = (a | b) != 0u;
+            const unsigned m = __ballot_sync(kFull, has);
+            if (m == 0u) break;
+            if (has) {
+                const int half = a ? 0 : 1;
+                const uint32_t w = a ? a : b;
+                const int bit = __ffs(w) - 1;
+                if (a) a &= a - 1;
+                else b &= b - 1;
+                const int o = 16 * (((bit >> 2) & 1) ^ 1) + 4 * (3 - (bit & 3)) + (bit >> 3);
+                hitlist[base + __popc(m & lt)] = (uint16_t)(half * 1024 + lane * 32 + o);
             }
+            base += __popc(m);
         }
         __syncwarp();
         uint32_t key = 0xFFFFFFFFu;
