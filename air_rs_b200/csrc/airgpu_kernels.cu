@@ -84,19 +84,19 @@ __device__ __forceinline__ uint32_t levels_u8_pair(uint32_t w, uint32_t minus_on
     return zsum + z1 * 65535u;                                // z0 + (z1 << 16)
 }
 
-// CS16: one 32-bit word = (re, im) little-endian i16.  Exact floor(sqrt(re^2+im^2)).
+// CS16: one 32-bit word = (re, im) little-endian i16.  Returns 65535 - floor(sqrt(re^2+im^2)), exactly.
+// MUFU gives sqrt to ~1e-2 absolute at this range (n <= 2^31); biasing it down by 0.02 makes the
+// truncated value r either the answer or one below it, so a single test of (r+1)^2 <= n finishes.
 __device__ __forceinline__ uint32_t level_cs16(uint32_t w)
 {
-    int re = (int)(short)(w & 0xFFFFu);
-    int im = ((int)w) >> 16;
-    uint32_t n = (uint32_t)(re * re) + (uint32_t)(im * im);     // <= 2^31
+    const int re = (int)__byte_perm(w, 0, 0x9910);      // sign-extended low half (one PRMT)
+    const int im = ((int)w) >> 16;
+    const uint32_t n = (uint32_t)(re * re) + (uint32_t)(im * im);
     float f;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(f) : "f"(__uint2float_rn(n)));
-    uint32_t r = __float2uint_rz(f);
-    int e = (int)(n - r * r);            // |r - isqrt(n)| <= 1, one correction step suffices
-    if (e < 0) r -= 1;
-    else if ((uint32_t)e > 2u * r) r += 1;
-    return 0xFFFFu - r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(__uint2float_rz(n)));
+    const uint32_t r = __float2uint_rz(f - 0.02f);      // negative -> 0
+    const uint32_t up = r * (r + 2u) + 1u;              // (r+1)^2 <= 46342^2 < 2^32
+    return (0xFFFFu - r) - (up <= n ? 1u : 0u);
 }
 
 template <int FMT>
@@ -496,6 +496,21 @@ __global__ void __launch_bounds__(kThreads, AIRGPU_MIN_CTAS) decode_kernel(const
         // and the shared address are "per-lane base + compile-time offset"
         const uint8_t *gsrc = src + lane * kChunkBytes;
         uint4 *sdst = reinterpret_cast<uint4 *>(lv) + (lane + (lane >> 3));
+        if (FMT == AIRGPU_FMT_CS16) {
+            // 2 x 16 bytes per chunk; rolled (fully unrolled it is 33 KB of code and misses the instruction cache)
+            uint4 a = ldg_stream(gsrc), b = ldg_stream(gsrc + 16);
+#pragma unroll 1
+            for (int m = 0; m < kWarpChunks / 32; ++m) {
+                uint4 na = a, nb = b;
+                if (m + 1 < kWarpChunks / 32) {
+                    na = ldg_stream(gsrc + 32 * (m + 1) * kChunkBytes);
+                    nb = ldg_stream(gsrc + 32 * (m + 1) * kChunkBytes + 16);
+                }
+                sdst[36 * m] = levels_of_chunk<FMT>(a, b, p.minus_one);
+                a = na;
+                b = nb;
+            }
+        } else {
         uint4 a[3], b[3], na[3], nb[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -522,6 +537,7 @@ __global__ void __launch_bounds__(kThreads, AIRGPU_MIN_CTAS) decode_kernel(const
                 a[j] = na[j];
                 b[j] = nb[j];
             }
+        }
         }
     } else {
         // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
