@@ -89,7 +89,7 @@ __device__ __forceinline__ uint32_t levels_u8_pair(uint32_t w, uint32_t minus_on
 // truncated value r either the answer or one below it, so a single test of (r+1)^2 <= n finishes.
 __device__ __forceinline__ uint32_t level_cs16(uint32_t w)
 {
-    const int re = (int)__byte_perm(w, 0, 0x9910);      // sign-extended low half (one PRMT)
+    const int re = (int)(short)(unsigned short)w;       // sign-extended low half
     const int im = ((int)w) >> 16;
     const uint32_t n = (uint32_t)(re * re) + (uint32_t)(im * im);
     float f;
