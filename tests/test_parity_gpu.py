@@ -380,3 +380,37 @@ def test_pipelined_sub_shards_equal_single_pass(dec_u8):
     got = frames.cpu().numpy().view(FRAME_DTYPE).reshape(-1)
     assert total == len(whole) and frames_equal(got, whole), describe_diff(got, whole)
     dev.close()
+
+
+def test_unaligned_device_pointer_and_odd_sizes(dec_u8, dec_cs16):
+    """device buffers that do not start on a 16-byte boundary take the guarded loader; odd lengths."""
+    import torch
+
+    for dec, maker, dt in ((dec_u8, capture_u8, torch.uint8), (dec_cs16, capture_cs16, torch.int16)):
+        _, iq = maker(seed=101, n=200_003)
+        big = torch.zeros(iq.size + 64, dtype=dt, device="cuda")
+        for shift in (0, 2, 6):                       # elements; 2 or 4 bytes each -> misaligned starts
+            view = big[shift : shift + iq.size]
+            view.copy_(torch.from_numpy(iq))
+            out, count = dec.decode_tensor(view, base_offset=(1 << 62) + 5, cap=1 << 15)
+            got = AdsbDecoder.frames_from_tensor(out, count)
+            want, _ = oracle_c.decode_fast(iq, 0, (1 << 62) + 5, threads=2)
+            assert frames_equal(got, want), describe_diff(got, want)
+
+
+def test_zero_capacity_and_exact_capacity(dec_u8):
+    from air_rs_b200 import native
+
+    _, iq = capture_u8(seed=102, n=300_000)
+    want, _ = oracle_c.decode_fast(iq, threads=2)
+    got = dec_u8.decode(iq, max_frames=len(want))      # exactly fits
+    assert frames_equal(got, want)
+    with pytest.raises(native.AirgpuError) as ei:
+        dec_u8.decode(iq, max_frames=len(want) - 1)
+    assert ei.value.code == native.ERR_OVERFLOW
+
+
+def test_many_tiny_segments(dec_cs16):
+    """thousands of independent 300-sample buffers in one call (60 candidates each)."""
+    _, iq = capture_cs16(seed=103, n=600_000, df17=6000.0)
+    check(dec_cs16, iq, seg=300)
