@@ -13,6 +13,7 @@ gloo in the CPU tests).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Tuple
 
 HALO = 240          # samples a candidate reads beyond its own offset, plus one (16 + 112*2)
@@ -104,7 +105,12 @@ class ShardedDecoder:
         self.dev = torch.device("cuda", decoder.device)
         cands = max(0, n_local - HALO)
         pieces = max(1, min(pieces, max(1, cands // ALIGN)))
-        b = [min(cands, (cands * k // pieces) // ALIGN * ALIGN) for k in range(pieces)] + [cands]
+        # later sub-shards are smaller: only the LAST exchange is exposed (nothing left to overlap it)
+        w = [float(pieces - k + 1) for k in range(pieces)] if pieces > 1 else [1.0]
+        if os.environ.get("AIRGPU_PIECE_WEIGHTS"):
+            w = [float(x) for x in os.environ["AIRGPU_PIECE_WEIGHTS"].split(",")][:pieces]
+        acc = [sum(w[:k]) / sum(w) for k in range(pieces)]
+        b = [min(cands, int(cands * a) // ALIGN * ALIGN) for a in acc] + [cands]
         self.ranges = [(b[k], b[k + 1]) for k in range(pieces)]   # same number of exchanges on every rank
         self.first = first_sample
         cap = cap_per_piece or max(1 << 14, (max(e - s for s, e in self.ranges) + HALO) // 200)   # ~4x dense traffic
