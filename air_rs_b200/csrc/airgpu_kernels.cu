@@ -21,14 +21,16 @@
 //             reference magnitudes, ties included.  Two IDP.4A per sample pair,
 //             no square root, no LUT.
 //       CS16: level = 65535 - isqrt(re^2 + im^2) (MUFU sqrt + integer fix-up).
-//   * the preamble test runs on packed u16x2 lanes (two offsets per
-//     instruction) with VIMNMX3.U16x2; a lane owns 16 consecutive offsets so the
-//     window lives in registers; warps leave the fast path only when some lane
-//     saw a preamble (5.6e-4 per offset on noise);
-//   * survivors are marked in a shared bitmap (order for free), sliced with warp
-//     ballots, checked with a 112-entry single-bit syndrome table, and appended
-//     with one global atomic per tile.
+//   * the preamble test runs on packed u16x2 words (two offsets per instruction,
+//     airgpu_scan.cuh): a warp tile is two streams of 1024 offsets and word w holds
+//     (level[w], level[1024 + w]); a lane owns 32 consecutive offsets of each stream
+//     so the window lives in registers; warps leave the fast path only when some
+//     lane saw a preamble (5.6e-4 per offset on noise);
+//   * survivors are spread over the lanes for the DF test, then sliced with warp
+//     ballots, checked with a 112-entry single-bit syndrome table and written to
+//     the tile's fixed scratch slots in offset order (no atomic with a return value).
 #include "airgpu_kernels.cuh"
+#include "airgpu_scan.cuh"
 
 namespace airgpu {
 namespace {
@@ -59,17 +61,6 @@ constexpr SynTable make_syn()
 }
 __device__ const SynTable g_syn = make_syn();
 
-// ---- shared-memory layout of the level array -------------------------------
-// Each warp owns kWarpLevels u16 levels in 16-byte chunks (8 levels).  Phase 1 writes
-// chunk c from lane c (stride 1), phase 2 reads chunks 2*lane + t (stride 2).  One
-// 16-byte pad after every 128 bytes keeps the stride-1 pattern conflict free and leaves
-// a single 2-way conflict in one of the four stride-2 loads; unlike an XOR swizzle it
-// keeps runs of consecutive levels at consecutive addresses, so the scalar readers (DF
-// test, bit slicer) pay the index arithmetic once per run instead of once per level.
-constexpr int kWarpLevelsPadded = kWarpLevels + 8 * (kWarpLevels / 64);
-__device__ __forceinline__ int phys_chunk(int c) { return c + (c >> 3); }
-__device__ __forceinline__ int phys_idx(int i) { return i + ((i >> 6) << 3); }
-
 // ---- per-sample level -------------------------------------------------------
 // U8: one 32-bit word = (I0, Q0, I1, Q1).  Returns (level0 | level1 << 16).
 __device__ __forceinline__ uint32_t levels_u8_pair(uint32_t w, uint32_t minus_one)
@@ -82,6 +73,20 @@ __device__ __forceinline__ uint32_t levels_u8_pair(uint32_t w, uint32_t minus_on
     const uint32_t zsum = __dp4a(nw, w, 0u);                  // z0 + z1
     const uint32_t z1 = __dp4a(nw, w & 0xFFFF0000u, 0u);      // z1
     return zsum + z1 * 65535u;                                // z0 + (z1 << 16)
+}
+
+// U8, two streams: wa = (I, Q, I', Q') of samples (s, s+1), wb = the same for samples (1024+s, 1024+s+1).
+// out0 = level[s] | level[1024+s] << 16, out1 = level[s+1] | level[1024+s+1] << 16.  Same instruction
+// count per sample as levels_u8_pair (4 IMAD + 4 IDP.4A + 2 LOP3 per four samples).
+__device__ __forceinline__ void levels_u8_streams(uint32_t wa, uint32_t wb, uint32_t minus_one, uint32_t &out0, uint32_t &out1)
+{
+    const uint32_t nwa = wa * minus_one + minus_one;            // ~wa on the FMA pipe
+    const uint32_t nwb = wb * minus_one + minus_one;
+    const uint32_t za1 = __dp4a(nwa, wa & 0xFFFF0000u, 0u);
+    const uint32_t zb1 = __dp4a(nwb, wb & 0xFFFF0000u, 0u);
+    out1 = zb1 * 65536u + za1;
+    const uint32_t sumb = __dp4a(nwb, wb, 0u);                  // zb0 + zb1
+    out0 = __dp4a(nwa, wa, sumb * 65536u - out1);               // (za0 + za1) + (zb0 + zb1) << 16 - out1
 }
 
 // CS16: one 32-bit word = (re, im) little-endian i16.  Returns 65535 - floor(sqrt(re^2+im^2)), exactly.
@@ -99,22 +104,26 @@ __device__ __forceinline__ uint32_t level_cs16(uint32_t w)
     return (0xFFFFu - r) - (up <= n ? 1u : 0u);
 }
 
+// Eight words of the tile from eight samples of each stream.
+// U8: a0 / b0 = the 16 bytes of stream 0 / 1 (a1, b1 unused); CS16: a0,a1 / b0,b1 = 2 x 16 bytes each.
 template <int FMT>
-__device__ __forceinline__ uint4 levels_of_chunk(uint4 a, uint4 b, uint32_t minus_one)
+__device__ __forceinline__ void words_of_chunk8(uint4 a0, uint4 a1, uint4 b0, uint4 b1, uint32_t minus_one, uint4 &o0, uint4 &o1)
 {
-    uint4 o;
-    if (FMT == AIRGPU_FMT_U8) {           // a = 8 samples, b unused
-        o.x = levels_u8_pair(a.x, minus_one);
-        o.y = levels_u8_pair(a.y, minus_one);
-        o.z = levels_u8_pair(a.z, minus_one);
-        o.w = levels_u8_pair(a.w, minus_one);
-    } else {                              // a, b = 4 samples each
-        o.x = level_cs16(a.x) | (level_cs16(a.y) << 16);
-        o.y = level_cs16(a.z) | (level_cs16(a.w) << 16);
-        o.z = level_cs16(b.x) | (level_cs16(b.y) << 16);
-        o.w = level_cs16(b.z) | (level_cs16(b.w) << 16);
+    if (FMT == AIRGPU_FMT_U8) {
+        levels_u8_streams(a0.x, b0.x, minus_one, o0.x, o0.y);
+        levels_u8_streams(a0.y, b0.y, minus_one, o0.z, o0.w);
+        levels_u8_streams(a0.z, b0.z, minus_one, o1.x, o1.y);
+        levels_u8_streams(a0.w, b0.w, minus_one, o1.z, o1.w);
+    } else {
+        o0.x = level_cs16(a0.x) | (level_cs16(b0.x) << 16);
+        o0.y = level_cs16(a0.y) | (level_cs16(b0.y) << 16);
+        o0.z = level_cs16(a0.z) | (level_cs16(b0.z) << 16);
+        o0.w = level_cs16(a0.w) | (level_cs16(b0.w) << 16);
+        o1.x = level_cs16(a1.x) | (level_cs16(b1.x) << 16);
+        o1.y = level_cs16(a1.y) | (level_cs16(b1.y) << 16);
+        o1.z = level_cs16(a1.z) | (level_cs16(b1.z) << 16);
+        o1.w = level_cs16(a1.w) | (level_cs16(b1.w) << 16);
     }
-    return o;
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const void *p)
@@ -136,42 +145,28 @@ __device__ __noinline__ uint4 load16_guarded(const uint8_t *src, long long off, 
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// bits 15 and 31 of the result are FAIL flags: set iff hi > lo in that u16 half, i.e.
-// the reference's "a high is below a low" (demod.rs:27-31) in the inverted level domain.
-template <int FMT>
-__device__ __forceinline__ uint32_t fail_bits(uint32_t lo, uint32_t hi)
+// Level `k` levels after candidate i's first sample: candidates of stream s = i >> 10 read the
+// (s ? high : low) u16 halves of consecutive words starting at word (i & 1023).
+__device__ __forceinline__ const uint16_t *level_ptr(const uint16_t *s16, int i, int k)
 {
-    if (FMT == AIRGPU_FMT_U8) {
-        // U8 levels are <= 0x7F00: read as bf16 they are finite, non-negative and ordered
-        // like the integers, subnormals included, so sign(lo - hi) is the comparison and a
-        // tie gives +0.  One HFMA2.BF16 on the FMA pipe instead of an integer-pipe op.
-        uint32_t d;
-        asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(0xBF80BF80u), "r"(lo));
-        return d;
-    } else {
-        bool ph, pl;
-        (void)__vibmax_u16x2(lo, hi, &ph, &pl);          // predicates: lo >= hi
-        return (ph ? 0u : 0x80000000u) | (pl ? 0u : 0x00008000u);
-    }
+    return s16 + 2 * phys_word((i & (kStream - 1)) + k) + (i >> 10);
 }
 
-__device__ __forceinline__ uint32_t lvl(const uint16_t *s, int i) { return s[phys_idx(i)]; }
-
 // DF = 17 test on the first five data bits (demod.rs:45-54), inverted levels.
-// Levels j..j+9 are consecutive in shared memory except that one pad (8 positions) may fall
-// inside the run (16 % of the hits).
-__device__ __forceinline__ bool df17_ok(const uint16_t *s, int i)
+// Words j..j+9 are consecutive in shared memory except that one pad (4 words) may fall inside the
+// run (28 % of the hits).
+__device__ __forceinline__ bool df17_ok(const uint16_t *s16, int i)
 {
-    const int j = i + 16;
-    const uint16_t *qa = s + phys_idx(j);
-    const int cross = 64 - (j & 63);      // first k that lies behind the pad (>= 10: none)
+    const int j = (i & (kStream - 1)) + 16;
+    const uint16_t *qa = level_ptr(s16, i, 16);
+    const int cross = 32 - (j & 31);      // first k that lies behind the pad (>= 10: none)
     uint32_t v[10];
     if (cross >= 10) {
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = qa[k];
+        for (int k = 0; k < 10; ++k) v[k] = qa[2 * k];
     } else {
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = qa[k + (k >= cross ? 8 : 0)];
+        for (int k = 0; k < 10; ++k) v[k] = qa[2 * k + (k >= cross ? 8 : 0)];
     }
     const uint32_t hi = max(max(max(v[0], v[3]), max(v[5], v[7])), v[8]);
     const uint32_t lo = min(min(min(v[1], v[2]), min(v[4], v[6])), v[9]);
@@ -193,18 +188,17 @@ __device__ __forceinline__ Cand process_candidate(const uint16_t *s, int i, int 
     uint32_t w[4];
     uint32_t syn_of[4];
     // lane handles bits k = lane + 32 r: levels j and j+1 with j = i + 16 + 2 k.  Consecutive
-    // rounds are 64 levels = 72 padded positions apart, so the two padded indices are computed
+    // rounds are 64 words = 72 padded words apart, so the two padded addresses are computed
     // once (the pair may straddle a pad, hence two of them).
-    const int j = i + 16 + 2 * lane;
-    const uint16_t *p0 = s + phys_idx(j);
-    const uint16_t *p1 = s + phys_idx(j + 1);
+    const uint16_t *p0 = level_ptr(s, i, 16 + 2 * lane);
+    const uint16_t *p1 = level_ptr(s, i, 17 + 2 * lane);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int k = 32 * r + lane;
         const bool act = (r < 3) || (lane < 16);              // k < 112
         bool bit = false;
         syn_of[r] = act ? __ldg(&g_syn.v[k]) : 0u;
-        if (act) bit = p0[72 * r] < p1[72 * r];                // m[2k] > m[2k+1]  (demod.rs:104)
+        if (act) bit = p0[144 * r] < p1[144 * r];                // m[2k] > m[2k+1]  (demod.rs:104)
         w[r] = __brev(__ballot_sync(kFull, bit));
         if (bit) part ^= syn_of[r];
     }
@@ -250,14 +244,6 @@ __device__ __forceinline__ unsigned long long record_word(const Cand &c, unsigne
     return which == 0 ? w0 : (which == 1 ? w1 : offset);
 }
 
-// 3-input packed min/max: VIMNMX3.U16x2 (64 lanes/clk/SM).  Splitting them into 2-input
-// VIMNMX.U16x2 + HMNMX2.BF16 pairs (each 128 lanes/clk/SM when issued alone) was measured
-// SLOWER in this mix: 0.903 ms vs 0.807 ms per 960 M samples.
-template <int FMT>
-__device__ __forceinline__ uint32_t min3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
-template <int FMT>
-__device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
-
 // Where the frames a warp finds go.  Every tile owns kSlotsPerTile fixed record slots in
 // scratch (slot index = tile * kSlotsPerTile), so the common case needs no reservation, no
 // atomic with a return value and no staging: records are written as they are found, in
@@ -292,74 +278,30 @@ __device__ __forceinline__ void emit_candidate(const uint16_t *lv, int i, int la
 // Gate + slice + CRC over the warp's candidates [0, wcands): the reference's offset
 // loop (adsb.rs:98-114) for this range, emitting in ascending offset order.
 //
-// The preamble test runs over the whole tile first (four 512-offset iterations, no
-// divergence); each lane only records WHICH of its offsets passed, as bits.  The DF test and
-// the survivors are then handled once per tile, so the cost of leaving the fast path is
-// paid once per 2048 offsets instead of once per 512 (in dense traffic nearly every
-// 512-offset block contains a real preamble).
+// The preamble test runs over the whole tile first (one straight-line pass, no divergence);
+// each lane only records WHICH of its 64 offsets passed, as bits.  The DF test and the
+// survivors are then handled once per tile, so the cost of leaving the fast path is paid once
+// per 2048 offsets (in dense traffic nearly every tile contains a real preamble).
 template <int FMT>
 __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hitlist, int wcands, int lane, Sink &sink)
 {
-    // A lane owns 32 consecutive offsets per iteration (two iterations of 1024 offsets per
-    // tile): the shared min/max arrays are computed once for 16 offset pairs instead of 8.
-    // hit bits of iteration it (pmA: it 0, pmB: it 1): offset it*1024 + lane*32 + 4*q + j
-    // (q = 0..7: which F register, j = 0..3: which byte of it) is bit 8*j + 7 - (q & 3) - 4*(q >> 2).
-    uint32_t pmA = 0u, pmB = 0u;
-    // window chunks 4*lane + c of iteration `it` sit at padded chunk pc[c] + 144*it
-    const uint4 *lv4 = reinterpret_cast<const uint4 *>(lv);
-    int pc[6];
+    // lane owns offsets x0 .. x0+31 of both streams, x0 = 32 * lane: words x0 .. x0+46, i.e.
+    // 16-byte chunks 8*lane .. 8*lane+11, which sit at padded chunks 9*lane + k + (k >> 3)
+    uint32_t pm[2];
+    {
+        const uint4 *lv4 = reinterpret_cast<const uint4 *>(lv) + 9 * lane;
+        uint32_t R[48];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) pc[c] = phys_chunk(4 * lane + c);
-    // fully unrolled: shared-memory offsets and hit-bit positions become immediates
-#pragma unroll
-    for (int it = 0; it < kWarpTile / 1024; ++it) {
-        if (it * 1024 >= wcands) break;
-        // E[t] = (level[ob+2t], level[ob+2t+1]) with ob = it*1024 + lane*32
-        uint32_t E[24];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const uint4 v = lv4[pc[c] + 144 * it];
-            E[4 * c + 0] = v.x;
-            E[4 * c + 1] = v.y;
-            E[4 * c + 2] = v.z;
-            E[4 * c + 3] = v.w;
+        for (int k = 0; k < 12; ++k) {
+            const uint4 v = lv4[k + (k >> 3)];
+            R[4 * k + 0] = v.x;
+            R[4 * k + 1] = v.y;
+            R[4 * k + 2] = v.z;
+            R[4 * k + 3] = v.w;
         }
-        uint32_t O[23], ME[23], MO[18], W[21];
-        // (measured alternative: O[t] on the FMA pipe via IMAD.WIDE + IMAD was slower, 0.633 vs 0.619 ms)
-#pragma unroll
-        for (int t = 0; t < 23; ++t) O[t] = __byte_perm(E[t], E[t + 1], 0x5432);   // (lvl[2t+1], lvl[2t+2])
-#pragma unroll
-        for (int t = 5; t < 23; ++t) ME[t] = __vminu2(E[t], O[t]);
-#pragma unroll
-        for (int t = 1; t < 18; ++t) MO[t] = __vminu2(O[t], E[t + 1]);
-#pragma unroll
-        for (int t = 5; t < 21; ++t) W[t] = min3u2<FMT>(ME[t], ME[t + 1], ME[t + 2]);
-        // For the offset pair (ob+2t, ob+2t+1):
-        //   highs 0,2,7,9               -> E[t], E[t+1], O[t+3], O[t+4]
-        //   lows  1 | 3..6 | 8 | 10..15 -> O[t] | MO[t+1], MO[t+2] | E[t+4] | W[t+5]
-        // F gathers the fail flags of four consecutive offsets (ob+4q .. ob+4q+3) into the
-        // top bits of its four bytes.
-        uint32_t fails[2] = {0u, 0u};    // [q >> 2], bit 8*j + 7 - (q & 3): offset ob + 4*q + j failed
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            uint32_t d[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = 2 * q + h;
-                const uint32_t hi = __vmaxu2(max3u2<FMT>(E[t], E[t + 1], O[t + 3]), O[t + 4]);
-                const uint32_t lo = min3u2<FMT>(min3u2<FMT>(O[t], MO[t + 1], MO[t + 2]), E[t + 4], W[t + 5]);
-                d[h] = fail_bits<FMT>(lo, hi);
-            }
-            const uint32_t F = __byte_perm(d[0], d[1], 0x7531);   // (d0.b1, d0.b3, d1.b1, d1.b3)
-            // keep bits 7..8-r of every byte, take bit 7-r from F (select: one LOP3)
-            const int r = q & 3;
-            const uint32_t keep = 0x01010101u * (0xFFu & ~(0xFFu >> r));
-            fails[q >> 2] = r == 0 ? F : ((fails[q >> 2] & keep) | ((F >> r) & ~keep));
-        }
-        const uint32_t hits = (~fails[0] & 0xF0F0F0F0u) | ((~fails[1] & 0xF0F0F0F0u) >> 4);
-        if (it == 0) pmA = hits;
-        else pmB = hits;
+        gate_scan<FMT == AIRGPU_FMT_U8>(R, pm);
     }
+    const uint32_t pmA = pm[0], pmB = pm[1];
 
     // ---- preamble hits of the whole tile ----
     const uint32_t nh = __popc(pmA) + __popc(pmB);
@@ -385,8 +327,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
                 const int bit = __ffs(w) - 1;
                 if (a) a &= a - 1;
                 else b &= b - 1;
-                const int o = 16 * (((bit >> 2) & 1) ^ 1) + 4 * (3 - (bit & 3)) + (bit >> 3);
-                hitlist[base + __popc(m & lt)] = (uint16_t)(half * 1024 + lane * 32 + o);
+                hitlist[base + __popc(m & lt)] = (uint16_t)(hit_stream(bit) * kStream + lane * kLaneX + hit_x(half, bit));
             }
             base += __popc(m);
         }
@@ -406,25 +347,25 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
     }
 
     // ---- many hits (degenerate input, e.g. a constant buffer): per-lane DF loops ----
-    uint32_t cmA = 0u, cmB = 0u;   // bit o: offset it*1024 + lane*32 + o passes the gate (A: it 0, B: it 1)
+    uint32_t cm[2] = {0u, 0u};   // cm[s] bit x: offset s*1024 + lane*32 + x passes the gate
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         uint32_t m = half ? pmB : pmA;
-        uint32_t c = 0u;
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            const int o = 16 * (((b >> 2) & 1) ^ 1) + 4 * (3 - (b & 3)) + (b >> 3);
-            const int i = half * 1024 + lane * 32 + o;
-            if (i < wcands && df17_ok(lv, i)) c |= 1u << o;
+            const int st = hit_stream(b), x = hit_x(half, b);
+            const int i = st * kStream + lane * kLaneX + x;
+            if (i < wcands && df17_ok(lv, i)) {
+                if (st) cm[1] |= 1u << x;
+                else cm[0] |= 1u << x;
+            }
         }
-        if (half) cmB = c;
-        else cmA = c;
     }
-    // survivors, in ascending offset order: iteration, then lane, then bit
+    // survivors, in ascending offset order: stream, then lane, then bit
 #pragma unroll 1
-    for (int it = 0; it < 2; ++it) {
-        const uint32_t mine = it ? cmB : cmA;
+    for (int st = 0; st < 2; ++st) {
+        const uint32_t mine = st ? cm[1] : cm[0];
         unsigned lanes = __ballot_sync(kFull, mine != 0u);
         while (lanes) {
             const int src_lane = __ffs(lanes) - 1;
@@ -433,7 +374,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
             while (bits) {
                 const int o = __ffs(bits) - 1;
                 bits &= bits - 1;
-                emit_candidate(lv, it * 1024 + src_lane * 32 + o, lane, sink);
+                emit_candidate(lv, st * kStream + src_lane * kLaneX + o, lane, sink);
             }
         }
     }
@@ -442,13 +383,17 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
 #ifndef AIRGPU_MIN_CTAS
 #define AIRGPU_MIN_CTAS 8
 #endif
+#ifndef AIRGPU_MIN_CTAS_CS16
+#define AIRGPU_MIN_CTAS_CS16 4       // ptxas then settles on ~70 registers without spills (7 CTAs per SM still fit); a cap of 64 or 72 spills
+#endif
 template <int FMT, bool kSingleSegment>
-__global__ void __launch_bounds__(kThreads, AIRGPU_MIN_CTAS) decode_kernel(const DecodeParams p)
+__global__ void __launch_bounds__(kThreads, FMT == AIRGPU_FMT_U8 ? AIRGPU_MIN_CTAS : AIRGPU_MIN_CTAS_CS16)
+decode_kernel(const DecodeParams p)
 {
     // Warps never talk to each other: each owns one tile (kWarpTile candidate offsets), a
     // private slice of shared memory, its own stage and its own output reservation.  The CTA
     // is only a packaging unit (4 warps keep the per-CTA footprint small: 8 CTAs per SM).
-    __shared__ __align__(128) uint16_t s_lvl[kWarps][kWarpLevelsPadded];
+    __shared__ __align__(128) uint16_t s_lvl[kWarps][2 * kTileWordsPadded];
     __shared__ uint16_t s_hits[kWarps][32];
 
     constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
@@ -488,69 +433,80 @@ __global__ void __launch_bounds__(kThreads, AIRGPU_MIN_CTAS) decode_kernel(const
     sink.gate = 0;
 
     // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
+    // Unit of work: 8 words of the tile = 8 samples of stream 0 (tile samples 8c ..) and 8 samples
+    // of stream 1 (1024 + 8c ..).  Words 1024 .. 1263 repeat, in their low halves, levels that
+    // words 0 .. 239 hold in their high halves: those loads hit L2.
     const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
-    if (p.vec_ok && rem >= (unsigned long long)kWarpLevels) {
-        // 9 chunks per lane in three batches; the loads of batch g+1 are in flight while
-        // batch g is converted, so a warp waits for HBM once per tile, not three times
-        // chunk c = lane + 32 m is stored at padded chunk (lane + lane/8) + 36 m: both the global
-        // and the shared address are "per-lane base + compile-time offset"
+    constexpr int kRounds = (kTileChunks8 + 31) / 32;           // 5; the last round has 30 units
+    constexpr int kStreamBytes = kStream * BPS;
+    if (p.vec_ok && rem >= (unsigned long long)(kStream + kTileWords)) {
+        // unit c = lane + 32 m: global address and shared address are both "per-lane base +
+        // compile-time offset" (padded 16-byte chunks 2c + (c >> 2) = 2 lane + (lane >> 2) + 72 m)
         const uint8_t *gsrc = src + lane * kChunkBytes;
-        uint4 *sdst = reinterpret_cast<uint4 *>(lv) + (lane + (lane >> 3));
+        uint4 *sdst = reinterpret_cast<uint4 *>(lv) + (2 * lane + (lane >> 2));
         if (FMT == AIRGPU_FMT_CS16) {
-            // 2 x 16 bytes per chunk; rolled (fully unrolled it is 33 KB of code and misses the instruction cache)
-            uint4 a = ldg_stream(gsrc), b = ldg_stream(gsrc + 16);
+            // rolled (fully unrolled it is far too much code for the instruction cache)
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            uint4 a0 = ldg_stream(gsrc), a1 = ldg_stream(gsrc + 16);
+            uint4 b0 = ldg_stream(gsrc + kStreamBytes), b1 = ldg_stream(gsrc + kStreamBytes + 16);
 #pragma unroll 1
-            for (int m = 0; m < kWarpChunks / 32; ++m) {
-                uint4 na = a, nb = b;
-                if (m + 1 < kWarpChunks / 32) {
-                    na = ldg_stream(gsrc + 32 * (m + 1) * kChunkBytes);
-                    nb = ldg_stream(gsrc + 32 * (m + 1) * kChunkBytes + 16);
+            for (int m = 0; m < kRounds; ++m) {
+                uint4 na0 = z, na1 = z, nb0 = z, nb1 = z;
+                if (m + 1 < kRounds && lane + 32 * (m + 1) < kTileChunks8) {
+                    const uint8_t *g = gsrc + 32 * (m + 1) * kChunkBytes;
+                    na0 = ldg_stream(g);
+                    na1 = ldg_stream(g + 16);
+                    nb0 = ldg_stream(g + kStreamBytes);
+                    nb1 = ldg_stream(g + kStreamBytes + 16);
                 }
-                sdst[36 * m] = levels_of_chunk<FMT>(a, b, p.minus_one);
-                a = na;
-                b = nb;
+                if (lane + 32 * m < kTileChunks8) {
+                    uint4 o0, o1;
+                    words_of_chunk8<FMT>(a0, a1, b0, b1, p.minus_one, o0, o1);
+                    sdst[72 * m] = o0;
+                    sdst[72 * m + 1] = o1;
+                }
+                a0 = na0;
+                a1 = na1;
+                b0 = nb0;
+                b1 = nb1;
             }
         } else {
-        uint4 a[3], b[3], na[3], nb[3];
+            // all ten loads of the lane are issued before the first conversion: a warp waits for
+            // HBM once per tile
+            uint4 a[kRounds], b[kRounds];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            a[j] = ldg_stream(gsrc + 32 * j * kChunkBytes);
-            if (FMT == AIRGPU_FMT_CS16) b[j] = ldg_stream(gsrc + 32 * j * kChunkBytes + 16);
-        }
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            if (g < 2) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int c = lane + 32 * (3 * (g + 1) + j);
-                    na[j] = ldg_stream(src + c * kChunkBytes);
-                    if (FMT == AIRGPU_FMT_CS16) nb[j] = ldg_stream(src + c * kChunkBytes + 16);
+            for (int m = 0; m < kRounds; ++m) {
+                if (32 * m + 31 < kTileChunks8 || lane + 32 * m < kTileChunks8) {
+                    a[m] = ldg_stream(gsrc + 32 * m * kChunkBytes);
+                    b[m] = ldg_stream(gsrc + 32 * m * kChunkBytes + kStreamBytes);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int c = lane + 32 * (3 * g + j);
-                *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a[j], b[j], p.minus_one);
+            for (int m = 0; m < kRounds; ++m) {
+                if (32 * m + 31 < kTileChunks8 || lane + 32 * m < kTileChunks8) {
+                    uint4 o0, o1;
+                    words_of_chunk8<FMT>(a[m], a[m], b[m], b[m], p.minus_one, o0, o1);
+                    sdst[72 * m] = o0;
+                    sdst[72 * m + 1] = o1;
+                }
             }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                a[j] = na[j];
-                b[j] = nb[j];
-            }
-        }
         }
     } else {
         // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
         const long long avail = (long long)rem * BPS;   // bytes to the end of the segment
-        const int need = min(kWarpChunks, (wcands + kFrameSamples + 7) / 8);
 #pragma unroll 1
-        for (int c = lane; c < kWarpChunks; c += 32) {
-            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-            if (c < need) {
-                a = load16_guarded(src, (long long)c * kChunkBytes, avail);
-                if (FMT == AIRGPU_FMT_CS16) b = load16_guarded(src, (long long)c * kChunkBytes + 16, avail);
+        for (int c = lane; c < kTileChunks8; c += 32) {
+            const long long oa = (long long)c * kChunkBytes, ob = oa + kStreamBytes;
+            uint4 a0 = load16_guarded(src, oa, avail), b0 = load16_guarded(src, ob, avail), a1 = a0, b1 = b0;
+            if (FMT == AIRGPU_FMT_CS16) {
+                a1 = load16_guarded(src, oa + 16, avail);
+                b1 = load16_guarded(src, ob + 16, avail);
             }
-            *reinterpret_cast<uint4 *>(&lv[phys_chunk(c) << 3]) = levels_of_chunk<FMT>(a, b, p.minus_one);
+            uint4 o0, o1;
+            words_of_chunk8<FMT>(a0, a1, b0, b1, p.minus_one, o0, o1);
+            uint4 *d = reinterpret_cast<uint4 *>(lv) + phys_chunk4(2 * c);
+            d[0] = o0;
+            d[1] = o1;
         }
     }
     __syncwarp();
@@ -735,7 +691,14 @@ __global__ void __launch_bounds__(256) fields_kernel(const unsigned long long *f
 __global__ void levels_u8_kernel(uint16_t *out, uint32_t minus_one)
 {
     unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = I | Q << 8
-    if (idx < 65536u) out[idx] = (uint16_t)(levels_u8_pair(idx, minus_one) & 0xFFFFu);
+    if (idx >= 65536u) return;
+    // the decode kernel's own arithmetic, both output positions and both streams must agree
+    uint32_t o0, o1, p0, p1;
+    levels_u8_streams(idx | (idx << 16), (idx ^ 0x5A5Au) * 0x10001u, minus_one, o0, o1);
+    levels_u8_streams((idx ^ 0xA5A5u) * 0x10001u, idx | (idx << 16), minus_one, p0, p1);
+    const uint32_t v = o0 & 0xFFFFu;
+    const bool same = (o1 & 0xFFFFu) == v && (p0 >> 16) == v && (p1 >> 16) == v && v == (levels_u8_pair(idx, minus_one) & 0xFFFFu);
+    out[idx] = same ? (uint16_t)v : (uint16_t)0xFFFFu;
 }
 
 __global__ void levels_cs16_kernel(const uint32_t *iq, unsigned long long n, uint16_t *out)

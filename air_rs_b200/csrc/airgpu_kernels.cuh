@@ -16,10 +16,7 @@ namespace airgpu {
 // ---- tiling ---------------------------------------------------------------
 // A warp is the unit of work: it owns kWarpTile consecutive candidate offsets and a
 // private slice of shared memory, so the hot loop has no CTA-wide barrier at all.
-constexpr int kWarpTile = 2048;                   // candidate offsets per warp
-constexpr int kHalo = 256;                        // a candidate at i reads samples [i, i+240): 239 needed, 256 keeps 16-byte chunks
-constexpr int kWarpLevels = kWarpTile + kHalo;    // u16 levels staged per warp
-constexpr int kWarpChunks = kWarpLevels / 8;      // 16-byte chunks (8 levels each): 288 = 9 per lane
+constexpr int kWarpTile = 2048;                   // candidate offsets per warp: two streams of 1024 (airgpu_scan.cuh)
 constexpr int kThreads = 128;                     // 4 independent warps per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = kWarpTile;                  // ordering unit: one tile_tab entry per warp tile
