@@ -29,6 +29,9 @@
 //   * survivors are spread over the lanes for the DF test, then sliced with warp
 //     ballots, checked with a 112-entry single-bit syndrome table and written to
 //     the tile's fixed scratch slots in offset order (no atomic with a return value).
+#include <algorithm>
+#include <cstdlib>
+
 #include "airgpu_kernels.cuh"
 #include "airgpu_scan.cuh"
 
@@ -138,11 +141,13 @@ __device__ __forceinline__ uint4 ldg_stream(const void *p)
 // 16 bytes at byte offset `off`, zero beyond `avail` bytes; any alignment (edge tiles only).
 __device__ __noinline__ uint4 load16_guarded(const uint8_t *src, long long off, long long avail)
 {
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    unsigned long long lo = 0ull, hi = 0ull;     // no indexed local array: the kernel keeps a zero-byte stack frame
 #pragma unroll 1
-    for (int b = 0; b < 16; ++b)
-        if (off + b < avail) w[b >> 2] |= (uint32_t)src[off + b] << (8 * (b & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    for (int b = 0; b < 8; ++b) {
+        if (off + b < avail) lo |= (unsigned long long)src[off + b] << (8 * b);
+        if (off + b + 8 < avail) hi |= (unsigned long long)src[off + b + 8] << (8 * b);
+    }
+    return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
 // Level `k` levels after candidate i's first sample: candidates of stream s = i >> 10 read the
@@ -380,49 +385,39 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
     }
 }
 
-#ifndef AIRGPU_MIN_CTAS
-#define AIRGPU_MIN_CTAS 8
-#endif
-#ifndef AIRGPU_MIN_CTAS_CS16
-#define AIRGPU_MIN_CTAS_CS16 4       // ptxas then settles on ~70 registers without spills (7 CTAs per SM still fit); a cap of 64 or 72 spills
-#endif
+// One tile = kWarpTile candidate offsets, done by one warp in its private slice of shared memory.
 template <int FMT, bool kSingleSegment>
-__global__ void __launch_bounds__(kThreads, FMT == AIRGPU_FMT_U8 ? AIRGPU_MIN_CTAS : AIRGPU_MIN_CTAS_CS16)
-decode_kernel(const DecodeParams p)
+__device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigned tile, const int lane, uint16_t *lv,
+                                            uint16_t *hitlist)
 {
-    // Warps never talk to each other: each owns one tile (kWarpTile candidate offsets), a
-    // private slice of shared memory, its own stage and its own output reservation.  The CTA
-    // is only a packaging unit (4 warps keep the per-CTA footprint small: 8 CTAs per SM).
-    __shared__ __align__(128) uint16_t s_lvl[kWarps][2 * kTileWordsPadded];
-    __shared__ uint16_t s_hits[kWarps][32];
-
     constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
     constexpr int kChunkBytes = 8 * BPS;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
 
     // Geometry.  `rem` = samples from this warp's first sample to the end of its segment;
-    // everything else follows from it.  The single-segment case (a long capture) avoids the
-    // division; all tile starts are multiples of 2048 samples, so 16-byte alignment of the
-    // loads is a per-launch property (p.vec_ok, computed by the host).
-    const unsigned tile = blockIdx.x * kWarps + warp;
-    if (tile >= p.n_tiles) return;
-    unsigned seg = 0, tile_in_seg = tile;
-    if (!kSingleSegment) {
-        seg = tile / p.tiles_per_seg;
-        tile_in_seg = tile - seg * p.tiles_per_seg;
+    // everything else follows from it.  All tile starts are multiples of 2048 samples, so
+    // 16-byte alignment of the loads is a per-launch property (p.vec_ok, computed by the host).
+    // Tiles below p.full_tiles (single-segment launches: all but the last two) are complete and
+    // need none of the 64-bit arithmetic.
+    unsigned long long seg_start = 0, wpos = (unsigned long long)tile * kWarpTile;
+    unsigned long long rem = (unsigned long long)(kStream + kTileWords);
+    int wcands = kWarpTile;
+    if (!kSingleSegment || tile >= p.full_tiles) {
+        unsigned seg = 0, tile_in_seg = tile;
+        if (!kSingleSegment) {
+            seg = tile / p.tiles_per_seg;
+            tile_in_seg = tile - seg * p.tiles_per_seg;
+        }
+        seg_start = kSingleSegment ? 0ull : (unsigned long long)seg * p.seg_len;
+        const unsigned long long seg_n = kSingleSegment ? p.n_samples : min(p.seg_len, p.n_samples - seg_start);
+        wpos = (unsigned long long)tile_in_seg * kWarpTile;
+        rem = seg_n > wpos ? seg_n - wpos : 0ull;
+        wcands = rem > (unsigned long long)kFrameSamples
+                     ? (int)min((unsigned long long)kWarpTile, rem - kFrameSamples) : 0;
     }
-    const unsigned long long seg_start = kSingleSegment ? 0ull : (unsigned long long)seg * p.seg_len;
-    const unsigned long long seg_n = kSingleSegment ? p.n_samples : min(p.seg_len, p.n_samples - seg_start);
-    const unsigned long long wpos = (unsigned long long)tile_in_seg * kWarpTile;
-    const unsigned long long rem = seg_n > wpos ? seg_n - wpos : 0ull;
-    const int wcands = rem > (unsigned long long)kFrameSamples
-                           ? (int)min((unsigned long long)kWarpTile, rem - kFrameSamples) : 0;
     if (wcands == 0) {
         if (lane == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
         return;
     }
-    uint16_t *lv = s_lvl[warp];
     unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
     Sink sink;
     sink.slots = scratch + (unsigned long long)tile * (kSlotsPerTile * 3);
@@ -512,7 +507,7 @@ decode_kernel(const DecodeParams p)
     __syncwarp();
 
     // ---- phase 2+3: gate, slice, CRC; frames go straight to the tile's scratch slots ----
-    scan_warp_range<FMT>(lv, s_hits[warp], wcands, lane, sink);
+    scan_warp_range<FMT>(lv, hitlist, wcands, lane, sink);
     const uint32_t nvalid = sink.seq;
 
     // ---- phase 4: publish the count (no atomic with a return value on the common path) ----
@@ -532,7 +527,35 @@ decode_kernel(const DecodeParams p)
         sink.ovf_room = p.ovf_cap > ovf_base ? p.ovf_cap - ovf_base : 0ull;
         sink.seq = 0;
         sink.gate = 0;
-        scan_warp_range<FMT>(lv, s_hits[warp], wcands, lane, sink);
+        scan_warp_range<FMT>(lv, hitlist, wcands, lane, sink);
+    }
+}
+
+#ifndef AIRGPU_MIN_CTAS
+#define AIRGPU_MIN_CTAS 8
+#endif
+#ifndef AIRGPU_MIN_CTAS_CS16
+#define AIRGPU_MIN_CTAS_CS16 4       // ptxas then settles on ~70 registers without spills (7 CTAs per SM still fit); a cap of 64 or 72 spills
+#endif
+template <int FMT, bool kSingleSegment>
+__global__ void __launch_bounds__(kThreads, FMT == AIRGPU_FMT_U8 ? AIRGPU_MIN_CTAS : AIRGPU_MIN_CTAS_CS16)
+decode_kernel(const DecodeParams p)
+{
+    // Warps never talk to each other: each owns one tile at a time, a private slice of shared
+    // memory and its own output slots.  The CTA is only a packaging unit (4 warps keep the
+    // per-CTA footprint small: 8 CTAs per SM).  A warp does p.tiles_per_warp tiles in a row
+    // (a CTA covers 4 * tiles_per_warp consecutive tiles, the four warps always on neighbouring
+    // ones): a warp's start-up (special registers, parameter loads, CTA launch) took 20 % of its
+    // life with one tile per warp.
+    __shared__ __align__(128) uint16_t s_lvl[kWarps][2 * kTileWordsPadded];
+    __shared__ uint16_t s_hits[kWarps][32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned tile = blockIdx.x * (kWarps * p.tiles_per_warp) + warp;
+#pragma unroll 1
+    for (unsigned rep = 0; rep < p.tiles_per_warp && tile < p.n_tiles; ++rep, tile += kWarps) {
+        decode_tile<FMT, kSingleSegment>(p, tile, lane, s_lvl[warp], s_hits[warp]);
+        __syncwarp();    // every lane is done reading the slice before the next tile overwrites it
     }
 }
 
@@ -709,11 +732,24 @@ __global__ void levels_cs16_kernel(const uint32_t *iq, unsigned long long n, uin
 
 }  // namespace
 
-cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream)
+cudaError_t launch_decode(int format, const DecodeParams &params, cudaStream_t stream)
 {
-    if (p.n_tiles == 0) return cudaSuccess;
-    const unsigned grid = (p.n_tiles + kWarps - 1) / kWarps;
+    if (params.n_tiles == 0) return cudaSuccess;
+    DecodeParams p = params;
     const bool single = p.tiles_per_seg >= p.n_tiles;     // one segment: no per-tile division
+    // complete tiles of a single-segment launch: tile * 2048 + 2288 <= n_samples
+    constexpr unsigned long long kSpan = kStream + kTileWords;
+    p.full_tiles = 0;
+    if (single && p.n_samples >= kSpan)
+        p.full_tiles = (unsigned)std::min<unsigned long long>(p.n_tiles, (p.n_samples - kSpan) / kWarpTile + 1);
+    // tiles per warp: amortise the warp start-up on long captures, keep every SM busy on short buffers
+    static const int forced = [] {
+        const char *e = std::getenv("AIRGPU_TILES_PER_WARP");
+        return e ? std::atoi(e) : 0;
+    }();
+    p.tiles_per_warp = forced > 0 ? (unsigned)forced : (p.n_tiles >= 131072u ? 4u : (p.n_tiles >= 32768u ? 2u : 1u));
+    const unsigned per_cta = kWarps * p.tiles_per_warp;
+    const unsigned grid = (p.n_tiles + per_cta - 1) / per_cta;
     if (format == AIRGPU_FMT_U8) {
         if (single) decode_kernel<AIRGPU_FMT_U8, true><<<grid, kThreads, 0, stream>>>(p);
         else decode_kernel<AIRGPU_FMT_U8, false><<<grid, kThreads, 0, stream>>>(p);

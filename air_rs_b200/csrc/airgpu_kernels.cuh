@@ -32,6 +32,8 @@ struct DecodeParams {
     unsigned int n_tiles;           // n_segments * tiles_per_seg
     unsigned int minus_one;         // 0xFFFFFFFF (see levels_u8_pair)
     unsigned int vec_ok;            // every warp slice starts 16-byte aligned (base aligned, seg_len % 8 == 0)
+    unsigned int full_tiles;        // set by launch_decode: leading tiles that are complete (single segment only)
+    unsigned int tiles_per_warp;    // set by launch_decode: consecutive rounds of tiles one warp decodes
     unsigned long long base_offset; // added to every frame offset
     airgpu_frame *scratch;          // n_tiles * kSlotsPerTile fixed slots, then ovf_cap overflow records
     unsigned long long cap;         // capacity of the final output
