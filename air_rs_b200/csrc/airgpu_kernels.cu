@@ -159,20 +159,16 @@ __device__ __forceinline__ const uint16_t *level_ptr(const uint16_t *s16, int i,
 
 // DF = 17 test on the first five data bits (demod.rs:45-54), inverted levels.
 // Words j..j+9 are consecutive in shared memory except that one pad (4 words) may fall inside the
-// run (28 % of the hits).
+// run (28 % of the hits); the pad is stepped over arithmetically so that lanes with and without it
+// run the same code.
 __device__ __forceinline__ bool df17_ok(const uint16_t *s16, int i)
 {
     const int j = (i & (kStream - 1)) + 16;
     const uint16_t *qa = level_ptr(s16, i, 16);
-    const int cross = 32 - (j & 31);      // first k that lies behind the pad (>= 10: none)
+    const int a = j & 31;
     uint32_t v[10];
-    if (cross >= 10) {
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = qa[2 * k];
-    } else {
-#pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = qa[2 * k + (k >= cross ? 8 : 0)];
-    }
+    for (int k = 0; k < 10; ++k) v[k] = qa[2 * k + (((a + k) >> 5) << 3)];
     const uint32_t hi = max(max(max(v[0], v[3]), max(v[5], v[7])), v[8]);
     const uint32_t lo = min(min(min(v[1], v[2]), min(v[4], v[6])), v[9]);
     return hi <= lo;
@@ -189,24 +185,26 @@ struct Cand {
 __device__ __forceinline__ Cand process_candidate(const uint16_t *s, int i, int lane)
 {
     Cand c;
-    uint32_t part = 0;
     uint32_t w[4];
     uint32_t syn_of[4];
     // lane handles bits k = lane + 32 r: levels j and j+1 with j = i + 16 + 2 k.  Consecutive
-    // rounds are 64 words = 72 padded words apart, so the two padded addresses are computed
-    // once (the pair may straddle a pad, hence two of them).
-    const uint16_t *p0 = level_ptr(s, i, 16 + 2 * lane);
-    const uint16_t *p1 = level_ptr(s, i, 17 + 2 * lane);
+    // rounds are 64 words = 72 padded words apart; level j+1 is the next word, one pad further
+    // when j is the last word before a pad.
+    const int wj = (i & (kStream - 1)) + 16 + 2 * lane;
+    const uint16_t *p0 = s + 2 * phys_word(wj) + (i >> 10);
+    const uint16_t *p1 = p0 + ((wj & 31) == 31 ? 10 : 2);
+    const bool tail = lane < 16;                                  // round 3 only has bits 96..111
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int k = 32 * r + lane;
-        const bool act = (r < 3) || (lane < 16);              // k < 112
-        bool bit = false;
-        syn_of[r] = act ? __ldg(&g_syn.v[k]) : 0u;
-        if (act) bit = p0[144 * r] < p1[144 * r];                // m[2k] > m[2k+1]  (demod.rs:104)
-        w[r] = __brev(__ballot_sync(kFull, bit));
-        if (bit) part ^= syn_of[r];
-    }
+    for (int r = 0; r < 4; ++r) syn_of[r] = (r < 3 || tail) ? __ldg(&g_syn.v[32 * r + lane]) : 0u;
+    // m[2k] > m[2k+1]  (demod.rs:104), inverted levels
+    const bool b0 = p0[0] < p1[0], b1 = p0[144] < p1[144], b2 = p0[288] < p1[288];
+    bool b3 = false;
+    if (tail) b3 = p0[432] < p1[432];
+    w[0] = __brev(__ballot_sync(kFull, b0));
+    w[1] = __brev(__ballot_sync(kFull, b1));
+    w[2] = __brev(__ballot_sync(kFull, b2));
+    w[3] = __brev(__ballot_sync(kFull, b3));
+    const uint32_t part = (b0 ? syn_of[0] : 0u) ^ (b1 ? syn_of[1] : 0u) ^ (b2 ? syn_of[2] : 0u) ^ (b3 ? syn_of[3] : 0u);
     const uint32_t syn = __reduce_xor_sync(kFull, part);
     c.fixed = 0xFFu;
     c.valid = true;
@@ -332,7 +330,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
                 const int bit = __ffs(w) - 1;
                 if (a) a &= a - 1;
                 else b &= b - 1;
-                hitlist[base + __popc(m & lt)] = (uint16_t)(hit_stream(bit) * kStream + lane * kLaneX + hit_x(half, bit));
+                hitlist[base + __popc(m & lt)] = (uint16_t)(hit_stream<FMT == AIRGPU_FMT_U8>(bit) * kStream + lane * kLaneX + hit_x<FMT == AIRGPU_FMT_U8>(half, bit));
             }
             base += __popc(m);
         }
@@ -359,7 +357,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            const int st = hit_stream(b), x = hit_x(half, b);
+            const int st = hit_stream<FMT == AIRGPU_FMT_U8>(b), x = hit_x<FMT == AIRGPU_FMT_U8>(half, b);
             const int i = st * kStream + lane * kLaneX + x;
             if (i < wcands && df17_ok(lv, i)) {
                 if (st) cm[1] |= 1u << x;

@@ -1,0 +1,20 @@
+"""CPU: the packed two-stream preamble gate of the decode kernel (csrc/airgpu_scan.cuh), compiled for the
+host, against a direct evaluation of the reference gate (demod.rs:17-44) on random level arrays -- both
+hit-bit gathering variants -- plus the hit-bit layout and the shared-memory bank-conflict pattern."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.parametrize("idp", [0, 1])
+def test_gate_scan_host_emulation(tmp_path, idp):
+    exe = tmp_path / f"emu_scan{idp}"
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-DAIRGPU_HITS_IDP={idp}", str(ROOT / "tools" / "emu_scan.cpp"), "-o", str(exe)],
+                   check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all equal" in r.stdout and "64 distinct of 64" in r.stdout
+    assert "phase-1 stores: worst 1-way" in r.stdout and "phase-2 loads: worst 1-way" in r.stdout

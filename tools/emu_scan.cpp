@@ -50,7 +50,7 @@ int main()
             std::set<int> got;
             for (int h = 0; h < 2; ++h)
                 for (int b = 0; b < 32; ++b)
-                    if (hits[h] >> b & 1) got.insert(hit_stream(b) * kStream + kLaneX * lane + hit_x(h, b));
+                    if (hits[h] >> b & 1) got.insert(hit_stream<true>(b) * kStream + kLaneX * lane + hit_x<true>(h, b));
             for (int s = 0; s < 2; ++s)
                 for (int x = 0; x < kLaneX; ++x) {
                     const int i = s * kStream + kLaneX * lane + x;
@@ -70,7 +70,7 @@ int main()
     // every (h, b) maps to a distinct (stream, x)
     std::set<int> seen;
     for (int h = 0; h < 2; ++h)
-        for (int b = 0; b < 32; ++b) seen.insert(hit_stream(b) * 64 + hit_x(h, b));
+        for (int b = 0; b < 32; ++b) seen.insert(hit_stream<true>(b) * 64 + hit_x<true>(h, b));
     printf("hit-bit map: %zu distinct of 64\n", seen.size());
 
     // bank conflicts
