@@ -90,6 +90,8 @@ __device__ __forceinline__ void levels_u8_streams(uint32_t wa, uint32_t wb, uint
     out1 = zb1 * 65536u + za1;
     const uint32_t sumb = __dp4a(nwb, wb, 0u);                  // zb0 + zb1
     out0 = __dp4a(nwa, wa, sumb * 65536u - out1);               // (za0 + za1) + (zb0 + zb1) << 16 - out1
+    // (measured alternative without the two masks -- sample 0 isolated by shifting both operands up
+    // 16 bits with multiplies, +2 FMA-pipe instructions per call -- was slower: 4.66 vs 4.36 ms)
 }
 
 // CS16: one 32-bit word = (re, im) little-endian i16.  Returns 65535 - floor(sqrt(re^2+im^2)), exactly.

@@ -145,8 +145,7 @@ AIRGPU_HD void gate_scan(const uint32_t (&R)[48], uint32_t (&hits)[2])
             }
             hits[h] = ((acc[3] * 256u + acc[2]) * 256u + acc[1]) * 256u + acc[0];
         }
-        return;
-    }
+    } else
 #endif
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
