@@ -414,3 +414,35 @@ def test_many_tiny_segments(dec_cs16):
     """thousands of independent 300-sample buffers in one call (60 candidates each)."""
     _, iq = capture_cs16(seed=103, n=600_000, df17=6000.0)
     check(dec_cs16, iq, seg=300)
+
+
+def test_several_tiles_per_warp(tmp_path):
+    """Long captures make a warp decode several tiles in a row (launch_decode picks 2 or 4 from 67 M samples
+    up).  Force 3 on small inputs -- a tile count that is not a multiple of 12, both formats, independent
+    segments -- in a fresh process (the knob is read once) and compare with the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, "tests")
+import numpy as np
+from air_rs_b200.decoder import AdsbDecoder
+from air_rs_b200.native import FMT_CS16, FMT_U8
+from oracle import oracle_c
+from common import capture_cs16, capture_u8, frames_equal, describe_diff
+for fmt, cap in ((FMT_U8, capture_u8), (FMT_CS16, capture_cs16)):
+    _, iq = cap(seed=77, n=333_333, df17=4000.0)
+    with AdsbDecoder(fmt=fmt, max_buffer_samples=1 << 20, max_frames=1 << 16) as d:
+        for seg in (0, 20_000, 5_000):
+            got = d.decode(iq, segment_samples=seg)
+            want, wgp = oracle_c.decode_fast(iq, seg, 0, threads=4)
+            assert frames_equal(got, want), describe_diff(got, want)
+            assert d.stats()["gate_passes"] == wgp
+            assert len(want) > 100
+print("ok")
+'''
+    env = dict(os.environ, AIRGPU_TILES_PER_WARP="3")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
