@@ -9,9 +9,10 @@
 //   1-bit repair   src/adsb/crc.rs:49-65
 //
 // Design:
-//   * one CTA per tile of kTile candidate offsets; IQ is read from HBM exactly
-//     once (+3% halo), with 16-byte coalesced loads; nothing but frame records
-//     is written back;
+//   * a WARP is the unit of work: one tile of kWarpTile candidate offsets at a time, in a
+//     private slice of shared memory (no __syncthreads anywhere); IQ is read from HBM once
+//     (the 240-sample halo of each stream comes from L2), with 16-byte coalesced loads;
+//     nothing but frame records is written back;
 //   * the per-sample "level" is kept in shared memory as u16 and is INVERTED
 //     (smaller level = larger magnitude):
 //       U8  : level = I*(255-I) + Q*(255-Q).  With re = (2I-255)*128 the
