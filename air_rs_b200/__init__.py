@@ -6,6 +6,8 @@ thread of the reference (src/adsb.rs:92-122).  This package holds
   native.py  ctypes binding of that ABI (fails loudly without the library / a GPU)
   decoder.py host-side mirror of the reference's decode-thread interface
   packet.py  AdsbPacket mirror (reference src/adsb/packet.rs, src/adsb/msgs.rs)
+  ingest.py  .c16 loader / writer and the playback thread (reference src/utils.rs, src/adsb.rs:75-89)
+  sharding.py  contiguous candidate shards + frame-list exchange for one process per GPU
   synth.py   integer-only synthetic capture generator (host) + device twin
 
 There is no CPU fallback in this package and it never imports oracle/.
