@@ -153,11 +153,10 @@ __device__ __noinline__ uint4 load16_guarded(const uint8_t *src, long long off, 
     return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
-// Level `k` levels after candidate i's first sample: candidates of stream s = i >> 10 read the
-// (s ? high : low) u16 halves of consecutive words starting at word (i & 1023).
+// Level `k` levels after candidate i's first sample (index arithmetic: airgpu_scan.cuh).
 __device__ __forceinline__ const uint16_t *level_ptr(const uint16_t *s16, int i, int k)
 {
-    return s16 + 2 * phys_word((i & (kStream - 1)) + k) + (i >> 10);
+    return s16 + level_index(i, k);
 }
 
 // DF = 17 test on the first five data bits (demod.rs:45-54), inverted levels.
@@ -167,11 +166,9 @@ __device__ __forceinline__ const uint16_t *level_ptr(const uint16_t *s16, int i,
 // per level; offsets are immediates).
 __device__ __forceinline__ bool df17_ok(const uint16_t *s16, int i)
 {
-    const int j = (i & (kStream - 1)) + 16;
     const uint16_t *qa = level_ptr(s16, i, 16);
-    const int a = j & 31;
     uint32_t v[10];
-    const int cross = 32 - a;                 // first k behind the pad (>= 10: none)
+    const int cross = df_cross(i);            // first k behind the pad (>= 10: none)
     const uint16_t *qb = qa + 8;
 #pragma unroll
     for (int k = 0; k < 10; ++k) v[k] = (k >= cross ? qb : qa)[2 * k];
@@ -197,16 +194,17 @@ __device__ __forceinline__ Cand process_candidate(const uint16_t *s, int i, int 
     // lane handles bits k = lane + 32 r: levels j and j+1 with j = i + 16 + 2 k.  Consecutive
     // rounds are 64 words = 72 padded words apart; level j+1 is the next word, one pad further
     // when j is the last word before a pad.
-    const int wj = (i & (kStream - 1)) + 16 + 2 * lane;
+    const int wj = slicer_word(i, lane);
     const uint16_t *p0 = s + 2 * phys_word(wj) + (i >> 10);
-    const uint16_t *p1 = p0 + ((wj & 31) == 31 ? 10 : 2);
+    const uint16_t *p1 = p0 + slicer_step(wj);
     const bool tail = lane < 16;                                  // round 3 only has bits 96..111
 #pragma unroll
     for (int r = 0; r < 4; ++r) syn_of[r] = (r < 3 || tail) ? __ldg(&g_syn.v[32 * r + lane]) : 0u;
     // m[2k] > m[2k+1]  (demod.rs:104), inverted levels
-    const bool b0 = p0[0] < p1[0], b1 = p0[144] < p1[144], b2 = p0[288] < p1[288];
+    const bool b0 = p0[0] < p1[0], b1 = p0[kSlicerRoundStride] < p1[kSlicerRoundStride],
+               b2 = p0[2 * kSlicerRoundStride] < p1[2 * kSlicerRoundStride];
     bool b3 = false;
-    if (tail) b3 = p0[432] < p1[432];
+    if (tail) b3 = p0[3 * kSlicerRoundStride] < p1[3 * kSlicerRoundStride];
     w[0] = __brev(__ballot_sync(kFull, b0));
     w[1] = __brev(__ballot_sync(kFull, b1));
     w[2] = __brev(__ballot_sync(kFull, b2));

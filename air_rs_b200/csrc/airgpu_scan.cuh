@@ -198,4 +198,21 @@ constexpr int kTileWordsPadded = kTileWords + 4 * ((kTileWords + 31) / 32);
 AIRGPU_HD int phys_chunk4(int c) { return c + (c >> 3); }
 AIRGPU_HD int phys_word(int w) { return w + ((w >> 5) << 2); }
 
+// ---- where the scalar readers find a level (indices into the tile's array viewed as u16) --------
+// Level `k` levels after candidate i's first sample: candidates of stream s = i >> 10 read the
+// (s ? high : low) u16 halves of consecutive words starting at word (i & 1023).
+AIRGPU_HD int level_index(int i, int k) { return 2 * phys_word((i & (kStream - 1)) + k) + (i >> 10); }
+
+// DF test (demod.rs:45-54): levels 16..25 of candidate i.  The ten words are consecutive except
+// that one pad (4 words = 8 u16) may fall inside the run; `cross` is the first k behind it
+// (>= 10: none).  Level k is at df_base + 2k, + 8 when k >= cross.
+AIRGPU_HD int df_cross(int i) { return 32 - (((i & (kStream - 1)) + 16) & 31); }
+
+// Slicer (demod.rs:92-131, 180-201): lane `lane` handles frame bits lane + 32 r, i.e. levels
+// 16 + 2k and 17 + 2k.  Rounds are 64 words = 72 padded words = 144 u16 apart; the second level
+// is the next word, one pad further when the first is the last word before a pad.
+AIRGPU_HD int slicer_word(int i, int lane) { return (i & (kStream - 1)) + 16 + 2 * lane; }
+AIRGPU_HD int slicer_step(int wj) { return (wj & 31) == 31 ? 10 : 2; }
+constexpr int kSlicerRoundStride = 144;
+
 }  // namespace airgpu

@@ -1,6 +1,7 @@
 """CPU: the packed two-stream preamble gate of the decode kernel (csrc/airgpu_scan.cuh), compiled for the
 host, against a direct evaluation of the reference gate (demod.rs:17-44) on random level arrays -- both
-hit-bit gathering variants -- plus the hit-bit layout and the shared-memory bank-conflict pattern."""
+hit-bit gathering variants -- plus the hit-bit layout, the shared-memory bank-conflict pattern, and the
+addresses the DF test and the bit slicer read (the same index helpers the kernel compiles)."""
 import subprocess
 from pathlib import Path
 
@@ -18,3 +19,4 @@ def test_gate_scan_host_emulation(tmp_path, idp):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all equal" in r.stdout and "64 distinct of 64" in r.stdout
     assert "phase-1 stores: worst 1-way" in r.stdout and "phase-2 loads: worst 1-way" in r.stdout
+    assert "level reads at the right address" in r.stdout

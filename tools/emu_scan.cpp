@@ -95,5 +95,46 @@ int main()
     for (int w = 0; w < kTileWords; ++w)
         if (phys_word(w) != 4 * phys_chunk4(w >> 2) + (w & 3)) { printf("phys mismatch at %d\n", w); return 1; }
     printf("phys_word == phys_chunk4 layout, padded words %d (max used %d)\n", kTileWordsPadded, phys_word(kTileWords - 1));
+
+    // the scalar readers: DF test and slicer addressing against the level they are meant to read
+    {
+        srand(99);
+        std::vector<uint32_t> L(2 * kStream + 240);
+        for (auto &v : L) v = (uint32_t)(rand() & 0xFFFF);
+        std::vector<uint16_t> S(2 * kTileWordsPadded, 0xDEAD);      // pads keep the sentinel
+        for (int w = 0; w < kTileWords; ++w) {
+            S[2 * phys_word(w)] = (uint16_t)L[w];
+            S[2 * phys_word(w) + 1] = (uint16_t)L[kStream + w];
+        }
+        int max_index = 0;
+        long long reads = 0;
+        for (int i = 0; i < 2 * kStream; ++i) {
+            const int base = level_index(i, 16), cross = df_cross(i);
+            for (int k = 0; k < 10; ++k) {
+                const int idx = base + 2 * k + (k >= cross ? 8 : 0);
+                if (S[idx] != (uint16_t)L[i + 16 + k]) { printf("DF address wrong: i %d k %d\n", i, k); return 1; }
+                max_index = idx > max_index ? idx : max_index;
+                reads++;
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                const int wj = slicer_word(i, lane);
+                const int i0 = 2 * phys_word(wj) + (i >> 10), i1 = i0 + slicer_step(wj);
+                for (int r = 0; r < 4; ++r) {
+                    const int k = lane + 32 * r;
+                    if (k >= 112) continue;                          // round 3 is predicated to lanes 0..15
+                    const int a = i0 + kSlicerRoundStride * r, b = i1 + kSlicerRoundStride * r;
+                    if (S[a] != (uint16_t)L[i + 16 + 2 * k] || S[b] != (uint16_t)L[i + 17 + 2 * k]) {
+                        printf("slicer address wrong: i %d bit %d\n", i, k);
+                        return 1;
+                    }
+                    max_index = b > max_index ? b : max_index;
+                    reads += 2;
+                }
+            }
+        }
+        printf("scalar readers: %lld level reads at the right address, max u16 index %d < %d\n", reads, max_index,
+               2 * kTileWordsPadded);
+        if (max_index >= 2 * kTileWordsPadded) return 1;
+    }
     return seen.size() == 64 ? 0 : 1;
 }
