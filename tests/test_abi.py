@@ -48,6 +48,11 @@ def test_sass_is_sm100_and_uses_packed_minmax():
     assert "sm_100a" in out
     assert "VIMNMX3.U16x2" in out and "IDP.4A" in out
     assert "airgpu" in out
+    # the U8 decode kernel: compare and hit-bit gathering on the FMA pipe, 16-byte streaming loads, no local memory
+    k = re.search(r"Function : \S*decode_kernelILi1ELb1E.*?(?=Function :|\Z)", out, flags=re.S).group(0)
+    assert "HSET2.BF16_V2" in k and "IDP.4A.S8.U8" in k and "LDG.E.NA.128" in k
+    assert " STL" not in k and " LDL" not in k
+    assert k.count("VIMNMX.U16x2") > 200 and "REDUX" in k
 
 
 def test_no_cpu_fallback(has_gpu):
