@@ -327,6 +327,9 @@ def run_ours(args):
         t0 = time.perf_counter()
         fast, _ = oracle_c.decode_fast(host, threads=ncores)
         dt_fast = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        fast1, _ = oracle_c.decode_fast(host, threads=1)
+        dt_fast1 = time.perf_counter() - t0
         # same frames as the GPU on that slice?
         out_host = AdsbDecoder.frames_from_tensor(out, n_frames_local)
         sub = out_host[out_host["offset"] < ns - HALO]
@@ -335,8 +338,10 @@ def run_ours(args):
             "sample": f"first {ns} samples ({ns / 2.4e6:.0f} s) of the same capture, literal C restatement of the "
                       "reference decode loop (the reference runs it on exactly one thread, src/adsb.rs:147)",
             "seconds": round(dt, 2),
+            "fast_one_core": {"value": round(ns / dt_fast1 / 1e6, 1), "cores": 1, "kind": "port (optimised)"},
             "fast_all_cores": {"value": round(ns / dt_fast / 1e6, 1), "cores": ncores, "kind": "port (optimised, chunk-parallel)"},
-            "gpu_frames_equal_cpu_frames_on_sample": bool(sub.tobytes() == lit.tobytes() and lit.tobytes() == fast.tobytes()),
+            "gpu_frames_equal_cpu_frames_on_sample": bool(sub.tobytes() == lit.tobytes() and lit.tobytes() == fast.tobytes()
+                                                          and fast1.tobytes() == fast.tobytes()),
             "frames_on_sample": int(len(lit)),
         }
 
