@@ -36,6 +36,17 @@ def test_every_declared_symbol_is_exported(header):
     assert set(names) <= bound, f"not bound in native.py: {sorted(set(names) - bound)}"
 
 
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers must compile as strict C99 and as C++ with nothing else included."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "include/airgpu.h"\n#include "include/airgpu_synth.h"\n'
+                   'int main(void) { airgpu_config c; airgpu_frame f; (void)c; (void)f; return sizeof(airgpu_frame) == 24 ? 0 : 1; }\n')
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only"],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++"]):
+        r = subprocess.run(cmd + [f"-I{ROOT}", str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_frame_record_layout():
     assert native.FRAME_DTYPE.itemsize == 24
     assert native.FRAME_DTYPE.fields["fixed_bit"][1] == 14
