@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -85,10 +86,10 @@ struct airgpu_ctx {
     bool ev_valid = false, evh_valid = false, evk_valid = false, sync_valid = false;
 
     // workspace shared by every decode on the compute stream (stream-ordered reuse)
-    airgpu_frame *scratch = nullptr;
-    size_t scratch_cap = 0;
+    void *scratch = nullptr;                   // kSlotBytes per slot
+    size_t scratch_cap = 0;                    // slots
     uint2 *tile_tab = nullptr;
-    unsigned long long *group_sum = nullptr;   // [overflow counter | frame sums | gate sums | bases], 1 + 3 * groups_cap
+    unsigned long long *group_sum = nullptr;   // [overflow counter | per-group sums | bases], 1 + 2 * groups_cap
     size_t groups_cap = 0;
     size_t tiles_cap = 0;
     unsigned long long *counters = nullptr;   // kNumCounters + 1 (last = running frame total)
@@ -105,6 +106,7 @@ struct airgpu_ctx {
     uint64_t next_ticket = 1, next_collect = 1;
 
     airgpu_stats stats{};
+    unsigned force_ordered = 0;                // AIRGPU_FORCE_ORDERED=1 (tests): every tile takes the ordered path
 };
 
 namespace {
@@ -121,7 +123,7 @@ int ensure_tiles(airgpu_ctx *c, size_t n_tiles)
     size_t want = std::max<size_t>(n_tiles, 1024);
     size_t groups = (want + kGroupTiles - 1) / kGroupTiles;
     CU(cudaMalloc(&c->tile_tab, want * sizeof(uint2)));
-    CU(cudaMalloc(&c->group_sum, (1 + 3 * groups) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->group_sum, (1 + 2 * groups) * sizeof(unsigned long long)));
     c->tiles_cap = want;
     c->groups_cap = groups;
     return AIRGPU_OK;
@@ -134,7 +136,7 @@ int ensure_scratch(airgpu_ctx *c, size_t cap)
     if (c->scratch) cudaFree(c->scratch);
     c->scratch = nullptr;
     c->scratch_cap = 0;
-    CU(cudaMalloc(&c->scratch, cap * sizeof(airgpu_frame)));
+    CU(cudaMalloc(&c->scratch, cap * (size_t)kSlotBytes));
     c->scratch_cap = cap;
     return AIRGPU_OK;
 }
@@ -167,7 +169,7 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     if ((rc = ensure_scratch(c, (size_t)g.n_tiles * kSlotsPerTile + ovf_cap)) != AIRGPU_OK) return rc;
 
     // the overflow index and the per-group sums restart with every piece (one memset: they are adjacent)
-    CU(cudaMemsetAsync(c->group_sum, 0, (1 + 2 * c->groups_cap) * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(c->group_sum, 0, (1 + c->groups_cap) * sizeof(unsigned long long), stream));
 
     DecodeParams p{};
     p.iq = d_iq;
@@ -185,8 +187,8 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.tile_tab = c->tile_tab;
     p.ovf_counter = c->group_sum;
     p.group_sum = c->group_sum + 1;
-    p.group_gate = c->group_sum + 1 + c->groups_cap;
-    p.group_base = c->group_sum + 1 + 2 * c->groups_cap;
+    p.group_base = c->group_sum + 1 + c->groups_cap;
+    p.force_ordered = c->force_ordered;
     CU(cudaEventRecord(c->evk0, stream));
     CU(launch_decode(c->format, p, stream));
     CU(cudaEventRecord(c->evk1, stream));
@@ -282,6 +284,7 @@ int airgpu_create(const airgpu_config *cfg, airgpu_ctx **out)
     c->format = (int)cfg->format;
     c->max_buffer_samples = cfg->max_buffer_samples ? cfg->max_buffer_samples : 262144;
     c->max_frames = cfg->max_frames ? cfg->max_frames : 8192;
+    if (const char *e = std::getenv("AIRGPU_FORCE_ORDERED")) c->force_ordered = std::atoi(e) ? 1u : 0u;
     unsigned n_slots = cfg->ring_slots ? cfg->ring_slots : 4;
 
 #define CUX(call)                                                                                 \

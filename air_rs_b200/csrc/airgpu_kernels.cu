@@ -63,7 +63,24 @@ constexpr SynTable make_syn()
     }
     return t;
 }
-__device__ const SynTable g_syn = make_syn();
+// The slicer gives lane l the frame bits 31 - l + 32 r (r = 0..3), so a lane needs exactly four
+// syndromes: one 16-byte load.  Entry .w is zero for the lanes that have no bit in round 3.
+struct SynLanes {
+    uint4 v[32];
+};
+constexpr SynLanes make_syn_lanes()
+{
+    const SynTable t = make_syn();
+    SynLanes s{};
+    for (int l = 0; l < 32; ++l) {
+        s.v[l].x = t.v[31 - l];
+        s.v[l].y = t.v[63 - l];
+        s.v[l].z = t.v[95 - l];
+        s.v[l].w = l >= 16 ? t.v[127 - l] : 0u;
+    }
+    return s;
+}
+__device__ const SynLanes g_syn_lanes = make_syn_lanes();
 
 // ---- per-sample level -------------------------------------------------------
 // U8: one 32-bit word = (I0, Q0, I1, Q1).  Returns (level0 | level1 << 16).
@@ -153,26 +170,18 @@ __device__ __noinline__ uint4 load16_guarded(const uint8_t *src, long long off, 
     return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
-// Level `k` levels after candidate i's first sample (index arithmetic: airgpu_scan.cuh).
-__device__ __forceinline__ const uint16_t *level_ptr(const uint16_t *s16, int i, int k)
+// DF = 17 test on the first five data bits (demod.rs:45-54), inverted levels, candidate = word xw
+// of stream st.  Words xw+16 .. xw+25 are consecutive in shared memory except that one pad (4 words
+// = 16 bytes) may fall inside the run (28 % of the hits): level k is read from one of two bases,
+// 16 bytes apart, chosen by k >= cross, so that lanes with and without a pad run the same code.
+__device__ __forceinline__ bool df17_ok(const uint16_t *s16, int xw, int st)
 {
-    return s16 + level_index(i, k);
-}
-
-// DF = 17 test on the first five data bits (demod.rs:45-54), inverted levels.
-// Words j..j+9 are consecutive in shared memory except that one pad (4 words = 16 bytes) may fall
-// inside the run (28 % of the hits): level k is read from one of two bases, 16 bytes apart, chosen
-// by k >= cross, so that lanes with and without a pad run the same code (two integer instructions
-// per level; offsets are immediates).
-__device__ __forceinline__ bool df17_ok(const uint16_t *s16, int i)
-{
-    const uint16_t *qa = level_ptr(s16, i, 16);
+    const uint16_t *qa = s16 + level_index(xw, st, 16);
     uint32_t v[10];
-    const int cross = df_cross(i);            // first k behind the pad (>= 10: none)
+    const int cross = df_cross(xw);            // first k behind the pad (>= 10: none)
     const uint16_t *qb = qa + 8;
 #pragma unroll
     for (int k = 0; k < 10; ++k) v[k] = (k >= cross ? qb : qa)[2 * k];
-    // (computing the step as ((a + k) >> 5) << 3 per level cost five instructions per level: 4.36 vs 4.28 ms)
     const uint32_t hi = max(max(max(v[0], v[3]), max(v[5], v[7])), v[8]);
     const uint32_t lo = min(min(min(v[1], v[2]), min(v[4], v[6])), v[9]);
     return hi <= lo;
@@ -184,187 +193,168 @@ struct Cand {
     bool valid;
 };
 
-// Warp-cooperative slice + CRC + repair for the candidate at offset i of the warp's
-// level array (demod.rs:65-82).  All lanes return the same value.
-__device__ __forceinline__ Cand process_candidate(const uint16_t *s, int i, int lane)
+// Warp-cooperative slice + CRC + repair for the candidate at word xw of stream st
+// (demod.rs:65-82).  All lanes return the same value.  Lane l owns frame bits 31 - l + 32 r, so
+// the four ballots ARE the big-endian frame words.
+__device__ __forceinline__ Cand process_candidate(const uint16_t *s, int xw, int st, int lane)
 {
     Cand c;
-    uint32_t w[4];
-    uint32_t syn_of[4];
-    // lane handles bits k = lane + 32 r: levels j and j+1 with j = i + 16 + 2 k.  Consecutive
-    // rounds are 64 words = 72 padded words apart; level j+1 is the next word, one pad further
-    // when j is the last word before a pad.
-    const int wj = slicer_word(i, lane);
-    const uint16_t *p0 = s + 2 * phys_word(wj) + (i >> 10);
+    const int wj = slicer_word(xw, lane);
+    const uint16_t *p0 = s + 2 * phys_word(wj) + st;
     const uint16_t *p1 = p0 + slicer_step(wj);
-    const bool tail = lane < 16;                                  // round 3 only has bits 96..111
-#pragma unroll
-    for (int r = 0; r < 4; ++r) syn_of[r] = (r < 3 || tail) ? __ldg(&g_syn.v[32 * r + lane]) : 0u;
+    const bool tail = lane >= 16;                                 // round 3 only has bits 96..111
+    const uint4 syn_of = __ldg(&g_syn_lanes.v[lane]);
     // m[2k] > m[2k+1]  (demod.rs:104), inverted levels
     const bool b0 = p0[0] < p1[0], b1 = p0[kSlicerRoundStride] < p1[kSlicerRoundStride],
                b2 = p0[2 * kSlicerRoundStride] < p1[2 * kSlicerRoundStride];
     bool b3 = false;
     if (tail) b3 = p0[3 * kSlicerRoundStride] < p1[3 * kSlicerRoundStride];
-    w[0] = __brev(__ballot_sync(kFull, b0));
-    w[1] = __brev(__ballot_sync(kFull, b1));
-    w[2] = __brev(__ballot_sync(kFull, b2));
-    w[3] = __brev(__ballot_sync(kFull, b3));
-    const uint32_t part = (b0 ? syn_of[0] : 0u) ^ (b1 ? syn_of[1] : 0u) ^ (b2 ? syn_of[2] : 0u) ^ (b3 ? syn_of[3] : 0u);
+    c.w0 = __ballot_sync(kFull, b0);
+    c.w1 = __ballot_sync(kFull, b1);
+    c.w2 = __ballot_sync(kFull, b2);
+    c.w3 = __ballot_sync(kFull, b3);
+    const uint32_t part = (b0 ? syn_of.x : 0u) ^ (b1 ? syn_of.y : 0u) ^ (b2 ? syn_of.z : 0u) ^ (b3 ? syn_of.w : 0u);
     const uint32_t syn = __reduce_xor_sync(kFull, part);
     c.fixed = 0xFFu;
     c.valid = true;
     if (syn != 0u) {
-        // crc.rs:49-65: only a flip of one of the 88 data bits can match
-        const unsigned m0 = __ballot_sync(kFull, syn_of[0] == syn);
-        const unsigned m1 = __ballot_sync(kFull, syn_of[1] == syn);
-        const unsigned m2 = __ballot_sync(kFull, lane < 24 && syn_of[2] == syn);
-        if (m0) {
-            c.fixed = __ffs(m0) - 1;
-            w[0] ^= 0x80000000u >> c.fixed;
-        } else if (m1) {
-            const int q = __ffs(m1) - 1;
-            c.fixed = 32 + q;
-            w[1] ^= 0x80000000u >> q;
-        } else if (m2) {
-            const int q = __ffs(m2) - 1;
-            c.fixed = 64 + q;
-            w[2] ^= 0x80000000u >> q;
-        } else {
+        // crc.rs:49-65: only a flip of one of the 88 data bits can match (round 2: bits 64..87 = lanes 8..31).
+        // Nearly every non-zero syndrome is unrepairable: one ballot settles that.
+        const bool h0 = syn_of.x == syn, h1 = syn_of.y == syn, h2 = lane >= 8 && syn_of.z == syn;
+        const unsigned any = __ballot_sync(kFull, h0 || h1 || h2);
+        if (any == 0u) {
             c.valid = false;
+        } else {
+            // the syndromes are distinct: exactly one (lane, round) matches.  Frame bit = 32 r + 31 - lane.
+            const int l = __ffs(any) - 1;
+            const int r = __shfl_sync(kFull, h0 ? 0 : (h1 ? 1 : 2), l);
+            c.fixed = 32 * r + 31 - l;
+            const uint32_t flip = 1u << l;
+            if (r == 0) c.w0 ^= flip;
+            else if (r == 1) c.w1 ^= flip;
+            else c.w2 ^= flip;
         }
     }
-    c.w0 = w[0];
-    c.w1 = w[1];
-    c.w2 = w[2];
-    c.w3 = w[3];
     return c;
 }
 
-// The three little-endian u64 words of an airgpu_frame record; lane `which` (0..2) gets its word.
-// Computed without branches: every lane forms all three and selects.
-__device__ __forceinline__ unsigned long long record_word(const Cand &c, unsigned long long offset, int which)
-{
-    const unsigned long long w0 = (unsigned long long)__byte_perm(c.w0, 0, 0x0123) |
-                                  ((unsigned long long)__byte_perm(c.w1, 0, 0x0123) << 32);
-    // bytes 12, 13 of the frame, then fixed_bit, then the reserved zero byte
-    const uint32_t hi = __byte_perm(c.w3, c.fixed, 0x7423);
-    const unsigned long long w1 = (unsigned long long)__byte_perm(c.w2, 0, 0x0123) | ((unsigned long long)hi << 32);
-    return which == 0 ? w0 : (which == 1 ? w1 : offset);
-}
-
-// Where the frames a warp finds go.  Every tile owns kSlotsPerTile fixed record slots in
-// scratch (slot index = tile * kSlotsPerTile), so the common case needs no reservation, no
-// atomic with a return value and no staging: records are written as they are found, in
-// offset order.  A tile with more frames than slots (degenerate input such as a constant
-// buffer) reserves an overflow range once and a second pass writes the rest there.
+// Where the frames a warp finds go.  Every tile owns kSlotsPerTile fixed 32-byte slots in scratch
+// (slot index = tile * kSlotsPerTile): the four big-endian frame words, then (offset within the
+// tile | fixed_bit << 16).  The common case therefore needs no reservation, no atomic with a return
+// value and no staging, and the fast path may fill the slots in ANY order -- gather_kernel ranks
+// the (at most kSlotsPerTile) records of a tile by offset.  A tile with more frames than slots
+// (degenerate input such as a constant buffer) is redone by the ordered path, which writes every
+// record in ascending offset order: the first kSlotsPerTile into the slots, the rest into an
+// overflow range reserved with one atomic.
 struct Sink {
-    unsigned long long *slots;      // this tile's fixed slots in scratch (u64 view)
-    unsigned long long *overflow;   // overflow range (u64 view), nullptr in pass 0
+    uint4 *slots;                   // this tile's fixed slots in scratch (2 x uint4 per slot)
+    uint4 *overflow;                // overflow range, nullptr on the fast path
     unsigned long long ovf_room;    // records that fit the overflow range
-    unsigned long long off0;        // frame offset of the warp's candidate 0
     uint32_t seq;                   // valid frames seen so far in this pass
     uint32_t gate;                  // gate passes (reference num_processed)
 };
 
-// One survivor of the gate: slice, CRC, repair, emit (warp-cooperative, warp-uniform i).
+// One survivor of the gate: slice, CRC, repair, emit (warp-cooperative, warp-uniform candidate).
 __device__ __forceinline__ void emit_candidate(const uint16_t *lv, int i, int lane, Sink &sink)
 {
-    sink.gate += 1;
-    const Cand c = process_candidate(lv, i, lane);
+    const Cand c = process_candidate(lv, i & (kStream - 1), i >> 10, lane);
     if (!c.valid) return;
-    if (sink.overflow == nullptr) {
-        if (sink.seq < (uint32_t)kSlotsPerTile && lane < 3)
-            sink.slots[sink.seq * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
-    } else if (sink.seq >= (uint32_t)kSlotsPerTile) {
+    uint4 *dst = nullptr;
+    if (sink.seq < (uint32_t)kSlotsPerTile) {
+        dst = sink.slots + 2 * sink.seq;
+    } else if (sink.overflow != nullptr) {
         const unsigned long long r = sink.seq - kSlotsPerTile;
-        if (lane < 3 && r < sink.ovf_room)
-            sink.overflow[r * 3 + lane] = record_word(c, sink.off0 + (unsigned)i, lane);
+        if (r < sink.ovf_room) dst = sink.overflow + 2 * r;
+    }
+    if (lane == 0 && dst != nullptr) {
+        dst[0] = make_uint4(c.w0, c.w1, c.w2, c.w3);
+        reinterpret_cast<uint32_t *>(dst + 1)[0] = (uint32_t)i | (c.fixed << 16);
     }
     sink.seq += 1;
 }
 
-// Gate + slice + CRC over the warp's candidates [0, wcands): the reference's offset
-// loop (adsb.rs:98-114) for this range, emitting in ascending offset order.
-//
-// The preamble test runs over the whole tile first (one straight-line pass, no divergence);
-// each lane only records WHICH of its 64 offsets passed, as bits.  The DF test and the
-// survivors are then handled once per tile, so the cost of leaving the fast path is paid once
-// per 2048 offsets (in dense traffic nearly every tile contains a real preamble).
+// The lane's 48 words of the tile -> one bit per owned offset that passes the preamble test.
 template <int FMT>
-__device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hitlist, int wcands, int lane, Sink &sink)
+__device__ __forceinline__ void gate_of_lane(const uint16_t *lv, int lane, uint32_t minus_one, uint32_t (&pm)[2])
 {
     // lane owns offsets x0 .. x0+31 of both streams, x0 = 32 * lane: words x0 .. x0+46, i.e.
     // 16-byte chunks 8*lane .. 8*lane+11, which sit at padded chunks 9*lane + k + (k >> 3)
-    uint32_t pm[2];
-    {
-        const uint4 *lv4 = reinterpret_cast<const uint4 *>(lv) + 9 * lane;
-        uint32_t R[48];
+    const uint4 *lv4 = reinterpret_cast<const uint4 *>(lv) + 9 * lane;
+    uint32_t R[48];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const uint4 v = lv4[k + (k >> 3)];
-            R[4 * k + 0] = v.x;
-            R[4 * k + 1] = v.y;
-            R[4 * k + 2] = v.z;
-            R[4 * k + 3] = v.w;
-        }
-        gate_scan<FMT == AIRGPU_FMT_U8>(R, pm);
+    for (int k = 0; k < 12; ++k) {
+        const uint4 v = lv4[k + (k >> 3)];
+        R[4 * k + 0] = v.x;
+        R[4 * k + 1] = v.y;
+        R[4 * k + 2] = v.z;
+        R[4 * k + 3] = v.w;
     }
-    const uint32_t pmA = pm[0], pmB = pm[1];
+    gate_scan<FMT == AIRGPU_FMT_U8>(R, pm, minus_one);
+}
 
-    // ---- preamble hits of the whole tile ----
-    const uint32_t nh = __popc(pmA) + __popc(pmB);
-    const uint32_t total_hits = __reduce_add_sync(kFull, nh);
-    if (total_hits == 0u) return;
-
-    if (total_hits <= 32u) {
-        // Usual case (a handful of hits per 2048 offsets): spread them over the lanes, one
-        // hit per lane, so the DF test runs once for all of them instead of once per hit of
-        // the busiest lane; survivors are then emitted in ascending offset order by repeated
-        // warp-wide minimum.
-        // one hit per lane and round; a round is one ballot (the list order is irrelevant, the
-        // emission below orders by offset)
-        uint32_t a = pmA, b = pmB, base = 0;
-        const uint32_t lt = (1u << lane) - 1u;
-        for (;;) {
-            const bool has = (a | b) != 0u;
-            const unsigned m = __ballot_sync(kFull, has);
-            if (m == 0u) break;
-            if (has) {
-                const int half = a ? 0 : 1;
-                const uint32_t w = a ? a : b;
-                const int bit = __ffs(w) - 1;
-                if (a) a &= a - 1;
-                else b &= b - 1;
-                hitlist[base + __popc(m & lt)] = (uint16_t)(hit_stream<FMT == AIRGPU_FMT_U8>(bit) * kStream + lane * kLaneX + hit_x<FMT == AIRGPU_FMT_U8>(half, bit));
-            }
-            base += __popc(m);
+// Gate + slice + CRC over the warp's candidates [0, wcands): the reference's offset loop
+// (adsb.rs:98-114) for this range.  FAST PATH: records are emitted in no particular order.
+//
+// The preamble test runs over the whole tile first (one straight-line pass, no divergence); each
+// lane only keeps WHICH of its 64 offsets passed, as bits.  Then, in rounds, every lane pops one of
+// its hits and runs the DF test on it (all lanes at once), and the survivors of the round are
+// sliced and checked one after the other by the whole warp.  A round costs the same whether one
+// lane or all of them have a hit; in dense traffic a tile has ~6 hits in ~1.3 rounds.
+template <int FMT>
+__device__ __forceinline__ void scan_tile_fast(const uint16_t *lv, int wcands, int lane, uint32_t minus_one, Sink &sink)
+{
+    uint32_t pm[2];
+    gate_of_lane<FMT>(lv, lane, minus_one, pm);
+    uint32_t a = pm[0], b = pm[1];
+    for (;;) {
+        const bool from_a = a != 0u;
+        const uint32_t w = from_a ? a : b;
+        if (__ballot_sync(kFull, w != 0u) == 0u) break;
+        int i = 0;
+        bool ok = false;
+        if (w != 0u) {
+            const int bit = __ffs(w) - 1;
+            const uint32_t rest = w & (w - 1u);
+            if (from_a) a = rest;
+            else b = rest;
+            const int xw = lane * kLaneX + hit_x(from_a ? 0 : 1, bit), st = hit_stream(bit);
+            i = st * kStream + xw;
+            ok = i < wcands && df17_ok(lv, xw, st);
         }
-        __syncwarp();
-        uint32_t key = 0xFFFFFFFFu;
-        if ((uint32_t)lane < total_hits) {
-            const int i = hitlist[lane];
-            if (i < wcands && df17_ok(lv, i)) key = (uint32_t)i;
+        unsigned surv = __ballot_sync(kFull, ok);
+        sink.gate += __popc(surv);
+        while (surv) {
+            const int src = __ffs(surv) - 1;
+            surv &= surv - 1u;
+            emit_candidate(lv, __shfl_sync(kFull, i, src), lane, sink);
         }
-        for (;;) {
-            const uint32_t next = __reduce_min_sync(kFull, key);
-            if (next == 0xFFFFFFFFu) break;
-            emit_candidate(lv, (int)next, lane, sink);
-            if (key == next) key = 0xFFFFFFFFu;
-        }
-        return;
     }
+}
 
-    // ---- many hits (degenerate input, e.g. a constant buffer): per-lane DF loops ----
+// The same range in ASCENDING OFFSET ORDER (adsb.rs:98): only for tiles with more frames than
+// fixed slots, i.e. degenerate input.  Not inlined: it must stay out of the hot loop's code.
+template <int FMT>
+__device__ __noinline__ unsigned long long scan_tile_ordered(const uint16_t *lv, int wcands, int lane, uint32_t minus_one,
+                                                             uint4 *slots, uint4 *overflow, unsigned long long ovf_room)
+{   // everything by value (a Sink passed by reference would live on the stack); returns gate passes << 32 | frames
+    Sink sink;
+    sink.slots = slots;
+    sink.overflow = overflow;
+    sink.ovf_room = ovf_room;
+    sink.seq = 0;
+    sink.gate = 0;
+    uint32_t pm[2];
+    gate_of_lane<FMT>(lv, lane, minus_one, pm);
     uint32_t cm[2] = {0u, 0u};   // cm[s] bit x: offset s*1024 + lane*32 + x passes the gate
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-        uint32_t m = half ? pmB : pmA;
+        uint32_t m = half ? pm[1] : pm[0];
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            const int st = hit_stream<FMT == AIRGPU_FMT_U8>(b), x = hit_x<FMT == AIRGPU_FMT_U8>(half, b);
-            const int i = st * kStream + lane * kLaneX + x;
-            if (i < wcands && df17_ok(lv, i)) {
+            const int st = hit_stream(b), x = hit_x(half, b);
+            const int xw = lane * kLaneX + x;
+            if (st * kStream + xw < wcands && df17_ok(lv, xw, st)) {
                 if (st) cm[1] |= 1u << x;
                 else cm[0] |= 1u << x;
             }
@@ -379,6 +369,7 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
             const int src_lane = __ffs(lanes) - 1;
             lanes &= lanes - 1;
             uint32_t bits = __shfl_sync(kFull, mine, src_lane);
+            sink.gate += __popc(bits);
             while (bits) {
                 const int o = __ffs(bits) - 1;
                 bits &= bits - 1;
@@ -386,12 +377,12 @@ __device__ __forceinline__ void scan_warp_range(const uint16_t *lv, uint16_t *hi
             }
         }
     }
+    return ((unsigned long long)sink.gate << 32) | sink.seq;
 }
 
 // One tile = kWarpTile candidate offsets, done by one warp in its private slice of shared memory.
 template <int FMT, bool kSingleSegment>
-__device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigned tile, const int lane, uint16_t *lv,
-                                            uint16_t *hitlist)
+__device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigned tile, const int lane, uint16_t *lv)
 {
     constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
     constexpr int kChunkBytes = 8 * BPS;
@@ -421,12 +412,11 @@ __device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigne
         if (lane == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
         return;
     }
-    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(p.scratch);
+    uint4 *scratch = reinterpret_cast<uint4 *>(p.scratch);
     Sink sink;
-    sink.slots = scratch + (unsigned long long)tile * (kSlotsPerTile * 3);
+    sink.slots = scratch + (unsigned long long)tile * (kSlotsPerTile * 2);
     sink.overflow = nullptr;
     sink.ovf_room = 0;
-    sink.off0 = p.base_offset + seg_start + wpos;
     sink.seq = 0;
     sink.gate = 0;
 
@@ -510,27 +500,32 @@ __device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigne
     __syncwarp();
 
     // ---- phase 2+3: gate, slice, CRC; frames go straight to the tile's scratch slots ----
-    scan_warp_range<FMT>(lv, hitlist, wcands, lane, sink);
-    const uint32_t nvalid = sink.seq;
-
-    // ---- phase 4: publish the count (no atomic with a return value on the common path) ----
-    unsigned long long ovf_base = 0;
-    if (lane == 0) {
-        if (nvalid) atomicAdd(&p.group_sum[tile / kGroupTiles], (unsigned long long)nvalid);            // RED
-        if (sink.gate) atomicAdd(&p.group_gate[tile / kGroupTiles], (unsigned long long)sink.gate);    // RED
-        if (nvalid > (uint32_t)kSlotsPerTile)
-            ovf_base = atomicAdd(p.ovf_counter, (unsigned long long)(nvalid - kSlotsPerTile));
-        p.tile_tab[tile] = make_uint2((unsigned)min(ovf_base, 0xFFFFFFFFull), nvalid);
+    uint32_t nvalid, gate;
+    if (!p.force_ordered) {
+        scan_tile_fast<FMT>(lv, wcands, lane, p.minus_one, sink);
+        nvalid = sink.seq;
+        gate = sink.gate;
+    } else {                                                               // tests only
+        const unsigned long long r = scan_tile_ordered<FMT>(lv, wcands, lane, p.minus_one, sink.slots, nullptr, 0ull);
+        nvalid = (uint32_t)r;
+        gate = (uint32_t)(r >> 32);
     }
+
+    // ---- phase 4: publish the tile's count ----
+    unsigned long long ovf_base = 0;
     if (nvalid > (uint32_t)kSlotsPerTile) {
-        // rare (degenerate input): second pass over the range writes frames kSlotsPerTile.. to
-        // the overflow area, which starts after all the fixed slots
+        // rare (degenerate input): redo the range in ascending offset order; frames kSlotsPerTile..
+        // go to the overflow area, which starts after all the fixed slots
+        if (lane == 0) ovf_base = atomicAdd(p.ovf_counter, (unsigned long long)(nvalid - kSlotsPerTile));
         ovf_base = __shfl_sync(kFull, ovf_base, 0);
-        sink.overflow = scratch + ((unsigned long long)p.n_tiles * kSlotsPerTile + ovf_base) * 3;
-        sink.ovf_room = p.ovf_cap > ovf_base ? p.ovf_cap - ovf_base : 0ull;
-        sink.seq = 0;
-        sink.gate = 0;
-        scan_warp_range<FMT>(lv, hitlist, wcands, lane, sink);
+        (void)scan_tile_ordered<FMT>(lv, wcands, lane, p.minus_one, sink.slots,
+                                     scratch + ((unsigned long long)p.n_tiles * kSlotsPerTile + ovf_base) * 2,
+                                     p.ovf_cap > ovf_base ? p.ovf_cap - ovf_base : 0ull);
+    }
+    if (lane == 0) {
+        p.tile_tab[tile] = make_uint2((unsigned)min(ovf_base, 0xFFFFFFFFull), nvalid);
+        // per-group sums, gate passes << 32 | frames: one fire-and-forget RED (no atomic with a return value)
+        if (gate) atomicAdd(&p.group_sum[tile / kGroupTiles], ((unsigned long long)gate << 32) | nvalid);
     }
 }
 
@@ -551,13 +546,18 @@ decode_kernel(const DecodeParams p)
     // ones): a warp's start-up (special registers, parameter loads, CTA launch) took 20 % of its
     // life with one tile per warp.
     __shared__ __align__(128) uint16_t s_lvl[kWarps][2 * kTileWordsPadded];
-    __shared__ uint16_t s_hits[kWarps][32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned tile = blockIdx.x * (kWarps * p.tiles_per_warp) + warp;
+    // (the bound is recomputed from the block index every round -- the volatile asm keeps ptxas from
+    // hoisting it: with 64 registers a loop counter or a hoisted bound is spilled to local memory)
 #pragma unroll 1
-    for (unsigned rep = 0; rep < p.tiles_per_warp && tile < p.n_tiles; ++rep, tile += kWarps) {
-        decode_tile<FMT, kSingleSegment>(p, tile, lane, s_lvl[warp], s_hits[warp]);
+    for (;;) {
+        unsigned cta;
+        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
+        if (tile >= min(p.n_tiles, (cta + 1) * (kWarps * p.tiles_per_warp))) break;
+        decode_tile<FMT, kSingleSegment>(p, tile, lane, s_lvl[warp]);
+        tile += kWarps;
         __syncwarp();    // every lane is done reading the slice before the next tile overwrites it
     }
 }
@@ -600,21 +600,21 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 }
 
 __global__ void __launch_bounds__(kScanThreads, 1)
-group_scan_kernel(const unsigned long long *group_sum, const unsigned long long *group_gate, unsigned n_groups,
-                  unsigned long long *group_base, unsigned long long *d_total, unsigned long long *d_gate)
+group_scan_kernel(const unsigned long long *group_sum, unsigned n_groups, unsigned long long *group_base,
+                  unsigned long long *d_total, unsigned long long *d_gate)
 {
     __shared__ unsigned long long s_warp[33];
     unsigned long long running = *d_total;   // frames already in `out` (pieces of one call append)
     unsigned long long gate = 0;
     for (unsigned base = 0; base < n_groups; base += kScanThreads) {
         const unsigned g = base + threadIdx.x;
-        const unsigned long long v = g < n_groups ? group_sum[g] : 0ull;
+        const unsigned long long both = g < n_groups ? group_sum[g] : 0ull;    // gate passes << 32 | frames
         unsigned long long total;
-        const unsigned long long excl = block_exclusive_scan(v, s_warp, &total);
+        const unsigned long long excl = block_exclusive_scan(both & 0xFFFFFFFFull, s_warp, &total);
         if (g < n_groups) group_base[g] = running + excl;
         running += total;
         unsigned long long gsum;
-        (void)block_exclusive_scan(g < n_groups ? group_gate[g] : 0ull, s_warp, &gsum);
+        (void)block_exclusive_scan(both >> 32, s_warp, &gsum);
         gate += gsum;
     }
     if (threadIdx.x == 0) {
@@ -623,19 +623,34 @@ group_scan_kernel(const unsigned long long *group_sum, const unsigned long long 
     }
 }
 
+// Scratch slot -> airgpu_frame (three little-endian u64 words): byte-swapped frame words, then
+// bytes 12, 13 | fixed_bit | reserved, then the absolute sample offset.
+__device__ __forceinline__ void store_record(unsigned long long *out, unsigned long long dst, const uint4 q, uint32_t meta,
+                                             unsigned long long tile_off0)
+{
+    const unsigned long long w0 = (unsigned long long)__byte_perm(q.x, 0, 0x0123) |
+                                  ((unsigned long long)__byte_perm(q.y, 0, 0x0123) << 32);
+    const uint32_t hi = __byte_perm(q.w, meta >> 16, 0x7423);
+    const unsigned long long w1 = (unsigned long long)__byte_perm(q.z, 0, 0x0123) | ((unsigned long long)hi << 32);
+    out[dst * 3 + 0] = w0;
+    out[dst * 3 + 1] = w1;
+    out[dst * 3 + 2] = tile_off0 + (meta & 0xFFFFu);
+}
+
 __global__ void __launch_bounds__(kGroupTiles)
-gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const unsigned long long *group_base,
-              unsigned n_tiles, unsigned long long *out, unsigned long long cap, unsigned long long ovf_cap)
+gather_kernel(const DecodeParams p, const unsigned long long *group_base, unsigned long long *out)
 {
     // One CTA per group of kGroupTiles tiles: scan the counts in shared memory, then one
-    // THREAD per output record (binary search for its tile) so that all record copies of the
-    // group are independent loads in flight at once.
+    // THREAD per record of the group (binary search for its tile) so that all record copies of
+    // the group are independent loads in flight at once.  The fast path of decode_kernel fills a
+    // tile's slots in no particular order: a record's place among the (at most kSlotsPerTile)
+    // records of its tile is the number of them with a smaller offset.
     __shared__ unsigned long long s_warp[33];
     __shared__ unsigned int s_excl[kGroupTiles + 1];
     __shared__ unsigned int s_ovf[kGroupTiles];
     const unsigned t0 = blockIdx.x * kGroupTiles;
     const unsigned t = t0 + threadIdx.x;
-    const uint2 e = t < n_tiles ? tile_tab[t] : make_uint2(0u, 0u);
+    const uint2 e = t < p.n_tiles ? p.tile_tab[t] : make_uint2(0u, 0u);
     unsigned long long total;
     const unsigned long long excl = block_exclusive_scan(e.y, s_warp, &total);
     if (total == 0) return;
@@ -644,6 +659,7 @@ gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const un
     if (threadIdx.x == 0) s_excl[kGroupTiles] = (unsigned)total;
     __syncthreads();
     const unsigned long long gbase = group_base[blockIdx.x];
+    const uint4 *scratch = reinterpret_cast<const uint4 *>(p.scratch);
     for (unsigned r = threadIdx.x; r < (unsigned)total; r += kGroupTiles) {
         // largest k with s_excl[k] <= r (tiles with zero frames share their successor's value)
         unsigned lo = 0, hi = kGroupTiles;
@@ -653,20 +669,34 @@ gather_kernel(const unsigned long long *scratch, const uint2 *tile_tab, const un
             else hi = mid;
         }
         const unsigned idx = r - s_excl[lo];
-        const unsigned long long dst = gbase + r;
-        if (dst >= cap) continue;
+        const unsigned n = s_excl[lo + 1] - s_excl[lo];
+        const unsigned tile = t0 + lo;
         unsigned long long src;
-        if (idx < (unsigned)kSlotsPerTile) {
-            src = (unsigned long long)(t0 + lo) * kSlotsPerTile + idx;
+        unsigned rank = idx;
+        if (n <= (unsigned)kSlotsPerTile) {
+            src = (unsigned long long)tile * kSlotsPerTile + idx;
+        } else if (idx < (unsigned)kSlotsPerTile) {           // ordered tile
+            src = (unsigned long long)tile * kSlotsPerTile + idx;
         } else {
             const unsigned long long o = (unsigned long long)s_ovf[lo] + (idx - kSlotsPerTile);
-            if (o >= ovf_cap) continue;
-            src = (unsigned long long)n_tiles * kSlotsPerTile + o;
+            if (o >= p.ovf_cap) continue;
+            src = (unsigned long long)p.n_tiles * kSlotsPerTile + o;
         }
-        const unsigned long long w0 = scratch[src * 3 + 0], w1 = scratch[src * 3 + 1], w2 = scratch[src * 3 + 2];
-        out[dst * 3 + 0] = w0;
-        out[dst * 3 + 1] = w1;
-        out[dst * 3 + 2] = w2;
+        const uint4 q = scratch[2 * src];
+        const uint32_t meta = reinterpret_cast<const uint32_t *>(scratch + 2 * src + 1)[0];
+        if (n <= (unsigned)kSlotsPerTile && n > 1u) {
+            rank = 0;
+            const uint4 *first = scratch + 2 * (unsigned long long)tile * kSlotsPerTile;
+            for (unsigned k = 0; k < n; ++k)
+                rank += (reinterpret_cast<const uint32_t *>(first + 2 * k + 1)[0] & 0xFFFFu) < (meta & 0xFFFFu) ? 1u : 0u;
+        }
+        const unsigned long long dst = gbase + s_excl[lo] + rank;
+        if (dst >= p.cap) continue;
+        // first sample of the tile: segments are p.seg_len apart, tiles kWarpTile apart inside one
+        const unsigned seg = tile / p.tiles_per_seg;
+        const unsigned long long off0 = p.base_offset + (unsigned long long)seg * p.seg_len +
+                                        (unsigned long long)(tile - seg * p.tiles_per_seg) * kWarpTile;
+        store_record(out, dst, q, meta, off0);
     }
 }
 
@@ -767,14 +797,12 @@ cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned l
                             cudaStream_t stream)
 {
     const unsigned n_groups = (p.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    group_scan_kernel<<<1, kScanThreads, 0, stream>>>(p.group_sum, p.group_gate, n_groups, p.group_base, d_total,
+    group_scan_kernel<<<1, kScanThreads, 0, stream>>>(p.group_sum, n_groups, p.group_base, d_total,
                                                        p.counters + kCounterGate);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (n_groups == 0) return cudaSuccess;
-    gather_kernel<<<n_groups, kGroupTiles, 0, stream>>>(reinterpret_cast<const unsigned long long *>(p.scratch),
-                                                        p.tile_tab, p.group_base, p.n_tiles,
-                                                        reinterpret_cast<unsigned long long *>(out), p.cap, p.ovf_cap);
+    gather_kernel<<<n_groups, kGroupTiles, 0, stream>>>(p, p.group_base, reinterpret_cast<unsigned long long *>(out));
     return cudaGetLastError();
 }
 

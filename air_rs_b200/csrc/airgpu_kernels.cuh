@@ -20,7 +20,8 @@ constexpr int kWarpTile = 2048;                   // candidate offsets per warp:
 constexpr int kThreads = 128;                     // 4 independent warps per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = kWarpTile;                  // ordering unit: one tile_tab entry per warp tile
-constexpr int kSlotsPerTile = 16;                 // fixed scratch record slots per tile; more frames than that go to the overflow area
+constexpr int kSlotsPerTile = 8;                  // fixed scratch slots per tile; more frames than that go to the overflow area
+constexpr int kSlotBytes = 32;                    // 4 big-endian frame words | offset in tile | fixed_bit << 16 | pad
 constexpr int kFrameSamples = 240;                // 16 + 112 * 2, reference src/adsb.rs:98
 constexpr int kGroupTiles = 256;                  // tiles per ordering group (one gather CTA)
 
@@ -34,15 +35,15 @@ struct DecodeParams {
     unsigned int vec_ok;            // every warp slice starts 16-byte aligned (base aligned, seg_len % 8 == 0)
     unsigned int full_tiles;        // set by launch_decode: leading tiles that are complete (single segment only)
     unsigned int tiles_per_warp;    // set by launch_decode: consecutive rounds of tiles one warp decodes
+    unsigned int force_ordered;     // tests: every tile takes the ordered (overflow) path
     unsigned long long base_offset; // added to every frame offset
-    airgpu_frame *scratch;          // n_tiles * kSlotsPerTile fixed slots, then ovf_cap overflow records
+    void *scratch;                  // n_tiles * kSlotsPerTile fixed slots of kSlotBytes, then ovf_cap overflow slots
     unsigned long long cap;         // capacity of the final output
     unsigned long long ovf_cap;     // capacity of the overflow area
     unsigned long long *counters;   // see the enum below
     unsigned long long *ovf_counter; // next free record of the overflow area (zeroed before the launch)
     uint2 *tile_tab;                // per tile: (overflow base, frame count)
-    unsigned long long *group_sum;  // per group of kGroupTiles tiles: frames (zeroed before the launch)
-    unsigned long long *group_gate; // per group: gate passes (zeroed before the launch)
+    unsigned long long *group_sum;  // per group of kGroupTiles tiles: gate passes << 32 | frames (zeroed before the launch)
     unsigned long long *group_base; // per group: ordered position of its first frame
 };
 

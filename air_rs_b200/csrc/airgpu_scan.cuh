@@ -22,10 +22,6 @@
 
 #include <cstdint>
 
-#ifndef AIRGPU_HITS_IDP
-#define AIRGPU_HITS_IDP 1     // 1: gather the hit bits with IDP.4A on the FMA pipe (bf16-comparable levels only; measured 4.37 vs 4.46 ms), 0: PRMT + LOP3 merge
-#endif
-
 #if defined(__CUDACC__)
 #define AIRGPU_HD __host__ __device__ __forceinline__
 #else
@@ -44,22 +40,13 @@ AIRGPU_HD uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 AIRGPU_HD uint32_t max2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 AIRGPU_HD uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 AIRGPU_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
-// bits 15 and 31: set iff hi > lo in that half.  The other bits are unspecified.
-template <bool kBf16>
-AIRGPU_HD uint32_t fail_bits(uint32_t lo, uint32_t hi)
+// 1 in every half where hi > lo, any 16-bit levels: max - lo is non-zero exactly there (no borrow
+// between the halves because max >= lo in each), clamped to 1.  The subtraction is written as
+// lo * minus_one + max so that it issues on the FMA pipe (minus_one = 0xFFFFFFFF is a kernel
+// parameter: ptxas cannot turn it back into an integer-pipe IADD3).
+AIRGPU_HD uint32_t fail_flags(uint32_t lo, uint32_t hi, uint32_t minus_one)
 {
-    if (kBf16) {
-        // levels <= 0x7F00 read as bf16 are finite, non-negative and ordered like the integers
-        // (subnormals included), so sign(lo - hi) is the comparison and a tie gives +0: one
-        // HFMA2.BF16 on the FMA pipe instead of an integer-pipe instruction
-        uint32_t d;
-        asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(0xBF80BF80u), "r"(lo));
-        return d;
-    } else {
-        bool ph, pl;
-        (void)__vibmax_u16x2(lo, hi, &ph, &pl);          // predicates: lo >= hi
-        return (ph ? 0u : 0x80000000u) | (pl ? 0u : 0x00008000u);
-    }
+    return __vminu2(lo * minus_one + __vmaxu2(hi, lo), 0x00010001u);
 }
 // 0xFFFF in every half where hi > lo (bf16 compare of valid, ordered level patterns)
 AIRGPU_HD uint32_t fail_mask_bf16(uint32_t lo, uint32_t hi)
@@ -75,6 +62,7 @@ AIRGPU_HD uint32_t dp4a_su(uint32_t a, uint32_t b, uint32_t c)
     asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
     return (uint32_t)d;
 }
+AIRGPU_HD uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
 #else
 inline uint32_t lo16(uint32_t a) { return a & 0xFFFFu; }
 inline uint32_t hi16(uint32_t a) { return a >> 16; }
@@ -91,11 +79,9 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
     for (int k = 0; k < 4; ++k) r |= (uint32_t)((v >> (8 * ((s >> (4 * k)) & 7))) & 0xFF) << (8 * k);
     return r;
 }
-template <bool kBf16>
-inline uint32_t fail_bits(uint32_t lo, uint32_t hi)
+inline uint32_t fail_flags(uint32_t lo, uint32_t hi, uint32_t minus_one)
 {
-    // the unspecified bits are filled with ones so that a consumer relying on them shows up
-    return 0x7FFF7FFFu | (hi16(hi) > hi16(lo) ? 0x80000000u : 0u) | (lo16(hi) > lo16(lo) ? 0x8000u : 0u);
+    return min2(lo * minus_one + max2(hi, lo), 0x00010001u);
 }
 inline uint32_t fail_mask_bf16(uint32_t lo, uint32_t hi)
 {
@@ -107,13 +93,26 @@ inline uint32_t dp4a_su(uint32_t a, uint32_t b, uint32_t c)
     for (int k = 0; k < 4; ++k) d += (int)(int8_t)(a >> (8 * k)) * (int)((b >> (8 * k)) & 0xFF);
     return (uint32_t)d;
 }
+inline uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    for (int k = 0; k < 4; ++k) c += ((a >> (8 * k)) & 0xFF) * ((b >> (8 * k)) & 0xFF);
+    return c;
+}
 #endif
 }  // namespace packed
 
 // R[d] = word x0 + d of the tile (d = 0 .. kLaneWords-1; R has 48 entries, the last is unused).
 // hits[h] bit b (h = 0, 1): the preamble test PASSED for stream hit_stream(b), offset x0 + hit_x(h, b).
+//
+// The hit bits are gathered on the FMA pipe: one dot product per offset pair adds that pair's two
+// bit weights (1 << e for stream 0, 16 << e for stream 1) into a byte-wide accumulator, so byte g of
+// hits[h] holds x = 16 h + 4 g .. + 3 of both streams.
+//   kBf16 (U8 levels, <= 0x7F00: valid, ordered bf16 patterns): HSET2.BF16 leaves 0xFFFF (two bytes
+//     of -1) per failing half; signed x unsigned dot products subtract the weights from -1.
+//   otherwise (CS16 levels use all 16 bits): fail_flags() leaves 1 per failing half; unsigned dot
+//     products add the weights up from 0 and the result is inverted once.
 template <bool kBf16>
-AIRGPU_HD void gate_scan(const uint32_t (&R)[48], uint32_t (&hits)[2])
+AIRGPU_HD void gate_scan(const uint32_t (&R)[48], uint32_t (&hits)[2], uint32_t minus_one)
 {
     using namespace packed;
     uint32_t P2[46], G[39], C[39];
@@ -123,71 +122,30 @@ AIRGPU_HD void gate_scan(const uint32_t (&R)[48], uint32_t (&hits)[2])
     for (int i = 0; i < 39; ++i) G[i] = max2(R[i], R[i + 2]);
 #pragma unroll
     for (int i = 0; i < 39; ++i) C[i] = min3(R[i + 1], P2[i + 3], P2[i + 5]);
-#if AIRGPU_HITS_IDP
-    if (kBf16) {
-        // Hit bits gathered on the FMA pipe: the compare leaves 0xFFFF (= two bytes of -1) per
-        // failing half, and one signed x unsigned dot product per offset pair subtracts that
-        // pair's two weights (1 << e for stream 0, 16 << e for stream 1) from a byte-wide
-        // accumulator.  Starting from -1, byte g of the result is ~(fail flags) of x = 4g .. 4g+3.
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t acc[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                acc[g] = g == 0 ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int x = 16 * h + 4 * g + e;
-                    const uint32_t hi = max2(G[x], G[x + 7]);
-                    const uint32_t lo = min3(C[x], C[x + 7], P2[x + 14]);
-                    acc[g] = dp4a_su(fail_mask_bf16(lo, hi), (1u << e) | (0x100000u << e), acc[g]);
-                }
-            }
-            hits[h] = ((acc[3] * 256u + acc[2]) * 256u + acc[1]) * 256u + acc[0];
-        }
-    } else
-#endif
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        uint32_t fails[2] = {0u, 0u};    // [g], bit 8*j + 7 - r: see below
+        uint32_t acc[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            uint32_t d[2];
+        for (int g = 0; g < 4; ++g) {
+            acc[g] = (kBf16 && g == 0) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int x = 2 * (8 * h + q) + e;
+            for (int e = 0; e < 4; ++e) {
+                const int x = 16 * h + 4 * g + e;
                 const uint32_t hi = max2(G[x], G[x + 7]);
                 const uint32_t lo = min3(C[x], C[x + 7], P2[x + 14]);
-                d[e] = fail_bits<kBf16>(lo, hi);
+                const uint32_t wgt = (1u << e) | (0x100000u << e);
+                if (kBf16) acc[g] = dp4a_su(fail_mask_bf16(lo, hi), wgt, acc[g]);
+                else acc[g] = dp4a_uu(fail_flags(lo, hi, minus_one), wgt, acc[g]);
             }
-            // top bits of the four bytes: (stream 0, x even), (stream 1, x even), (stream 0, x odd), (stream 1, x odd)
-            const uint32_t F = prmt(d[0], d[1], 0x7531);
-            // keep bits 7..8-r of every byte, take bit 7-r from F (select: one LOP3)
-            const int r = q & 3;
-            const uint32_t keep = 0x01010101u * (0xFFu & ~(0xFFu >> r));
-            fails[q >> 2] = r == 0 ? F : ((fails[q >> 2] & keep) | ((F >> r) & ~keep));
         }
-        hits[h] = (~fails[0] & 0xF0F0F0F0u) | ((~fails[1] & 0xF0F0F0F0u) >> 4);
+        const uint32_t v = ((acc[3] * 256u + acc[2]) * 256u + acc[1]) * 256u + acc[0];
+        hits[h] = kBf16 ? v : ~v;
     }
 }
 
 // bit b of hits[h]  ->  which stream, which of the lane's 32 offsets
-template <bool kBf16>
-AIRGPU_HD int hit_stream(int b)
-{
-#if AIRGPU_HITS_IDP
-    if (kBf16) return (b >> 2) & 1;
-#endif
-    return (b >> 3) & 1;
-}
-template <bool kBf16>
-AIRGPU_HD int hit_x(int h, int b)
-{
-#if AIRGPU_HITS_IDP
-    if (kBf16) return 16 * h + 4 * (b >> 3) + (b & 3);
-#endif
-    return 2 * (8 * h + 7 - (b & 7)) + (b >> 4);
-}
+AIRGPU_HD int hit_stream(int b) { return (b >> 2) & 1; }
+AIRGPU_HD int hit_x(int h, int b) { return 16 * h + 4 * (b >> 3) + (b & 3); }
 
 // ---- shared-memory layout of the word array ----------------------------------------------------
 // 16-byte chunks of 4 words; one pad chunk after every 8 keeps both access patterns conflict
@@ -199,19 +157,20 @@ AIRGPU_HD int phys_chunk4(int c) { return c + (c >> 3); }
 AIRGPU_HD int phys_word(int w) { return w + ((w >> 5) << 2); }
 
 // ---- where the scalar readers find a level (indices into the tile's array viewed as u16) --------
-// Level `k` levels after candidate i's first sample: candidates of stream s = i >> 10 read the
-// (s ? high : low) u16 halves of consecutive words starting at word (i & 1023).
-AIRGPU_HD int level_index(int i, int k) { return 2 * phys_word((i & (kStream - 1)) + k) + (i >> 10); }
+// Candidate = (stream st, word xw): offset i = st * kStream + xw reads the (st ? high : low) u16
+// halves of consecutive words starting at word xw.
+AIRGPU_HD int level_index(int xw, int st, int k) { return 2 * phys_word(xw + k) + st; }
 
-// DF test (demod.rs:45-54): levels 16..25 of candidate i.  The ten words are consecutive except
+// DF test (demod.rs:45-54): levels 16..25 of the candidate.  The ten words are consecutive except
 // that one pad (4 words = 8 u16) may fall inside the run; `cross` is the first k behind it
-// (>= 10: none).  Level k is at df_base + 2k, + 8 when k >= cross.
-AIRGPU_HD int df_cross(int i) { return 32 - (((i & (kStream - 1)) + 16) & 31); }
+// (>= 10: none).  Level k is at level_index(xw, st, 16) + 2k, + 8 when k >= cross.
+AIRGPU_HD int df_cross(int xw) { return 32 - ((xw + 16) & 31); }
 
-// Slicer (demod.rs:92-131, 180-201): lane `lane` handles frame bits lane + 32 r, i.e. levels
-// 16 + 2k and 17 + 2k.  Rounds are 64 words = 72 padded words = 144 u16 apart; the second level
-// is the next word, one pad further when the first is the last word before a pad.
-AIRGPU_HD int slicer_word(int i, int lane) { return (i & (kStream - 1)) + 16 + 2 * lane; }
+// Slicer (demod.rs:92-131, 180-201): lane `lane` handles frame bits 31 - lane + 32 r (so that a
+// ballot is the big-endian frame word as it stands), i.e. levels 16 + 2k and 17 + 2k.  Rounds are
+// 64 words = 72 padded words = 144 u16 apart; the second level is the next word, one pad further
+// when the first is the last word before a pad.  Round 3 only has bits 96..111: lanes 16..31.
+AIRGPU_HD int slicer_word(int xw, int lane) { return xw + 16 + 2 * (31 - lane); }
 AIRGPU_HD int slicer_step(int wj) { return (wj & 31) == 31 ? 10 : 2; }
 constexpr int kSlicerRoundStride = 144;
 

@@ -31,14 +31,17 @@ static int conflicts(const std::vector<int> &chunk_of_lane)   // 16-byte chunk i
     return worst;
 }
 
-int main()
+template <bool kBf16>
+static int check_gate()
 {
     long long checked = 0, passes = 0;
     for (int trial = 0; trial < 400; ++trial) {
         srand(1234 + trial);
         const int range = 2 + trial % 7;           // few distinct levels: many passes and many ties
         std::vector<uint32_t> L(2 * kStream + 240 + 64);
-        for (auto &v : L) v = 2u * (uint32_t)(rand() % range) * (trial % 3 == 0 ? 4000u : 1u);
+        // bf16-comparable levels stay <= 0x7F00; the generic compare must work on all 16 bits
+        const uint32_t scale = trial % 3 == 0 ? (kBf16 ? 2000u : 4095u) : 1u;   // 2 * 8 * scale fits the level range
+        for (auto &v : L) v = 2u * (uint32_t)(rand() % range) * scale + ((!kBf16 && scale == 1u && trial % 5 == 0) ? 0xFFE0u : 0u);
         std::vector<uint32_t> W(kTileWords + 64);
         for (int w = 0; w < kTileWords; ++w) W[w] = L[w] | (L[kStream + w] << 16);
         for (int lane = 0; lane < 32; ++lane) {
@@ -46,11 +49,11 @@ int main()
             for (int d = 0; d < 48; ++d) R[d] = W[kLaneX * lane + d];
             R[47] = 0xDEADBEEFu;                   // must not matter
             uint32_t hits[2];
-            gate_scan<true>(R, hits);
+            gate_scan<kBf16>(R, hits, 0xFFFFFFFFu);
             std::set<int> got;
             for (int h = 0; h < 2; ++h)
                 for (int b = 0; b < 32; ++b)
-                    if (hits[h] >> b & 1) got.insert(hit_stream<true>(b) * kStream + kLaneX * lane + hit_x<true>(h, b));
+                    if (hits[h] >> b & 1) got.insert(hit_stream(b) * kStream + kLaneX * lane + hit_x(h, b));
             for (int s = 0; s < 2; ++s)
                 for (int x = 0; x < kLaneX; ++x) {
                     const int i = s * kStream + kLaneX * lane + x;
@@ -65,12 +68,18 @@ int main()
             if (got.size() > 64) { printf("too many bits\n"); return 1; }
         }
     }
-    printf("gate_scan: %lld offsets checked, %lld passes, all equal\n", checked, passes);
+    printf("gate_scan<%s>: %lld offsets checked, %lld passes, all equal\n", kBf16 ? "bf16" : "u16", checked, passes);
+    return 0;
+}
+
+int main()
+{
+    if (check_gate<true>() || check_gate<false>()) return 1;
 
     // every (h, b) maps to a distinct (stream, x)
     std::set<int> seen;
     for (int h = 0; h < 2; ++h)
-        for (int b = 0; b < 32; ++b) seen.insert(hit_stream<true>(b) * 64 + hit_x<true>(h, b));
+        for (int b = 0; b < 32; ++b) seen.insert(hit_stream(b) * 64 + hit_x(h, b));
     printf("hit-bit map: %zu distinct of 64\n", seen.size());
 
     // bank conflicts
@@ -109,7 +118,8 @@ int main()
         int max_index = 0;
         long long reads = 0;
         for (int i = 0; i < 2 * kStream; ++i) {
-            const int base = level_index(i, 16), cross = df_cross(i);
+            const int xw = i & (kStream - 1), st = i >> 10;
+            const int base = level_index(xw, st, 16), cross = df_cross(xw);
             for (int k = 0; k < 10; ++k) {
                 const int idx = base + 2 * k + (k >= cross ? 8 : 0);
                 if (S[idx] != (uint16_t)L[i + 16 + k]) { printf("DF address wrong: i %d k %d\n", i, k); return 1; }
@@ -117,11 +127,11 @@ int main()
                 reads++;
             }
             for (int lane = 0; lane < 32; ++lane) {
-                const int wj = slicer_word(i, lane);
-                const int i0 = 2 * phys_word(wj) + (i >> 10), i1 = i0 + slicer_step(wj);
+                const int wj = slicer_word(xw, lane);
+                const int i0 = 2 * phys_word(wj) + st, i1 = i0 + slicer_step(wj);
                 for (int r = 0; r < 4; ++r) {
-                    const int k = lane + 32 * r;
-                    if (k >= 112) continue;                          // round 3 is predicated to lanes 0..15
+                    const int k = 31 - lane + 32 * r;
+                    if (k >= 112) continue;                          // round 3 is predicated to lanes 16..31
                     const int a = i0 + kSlicerRoundStride * r, b = i1 + kSlicerRoundStride * r;
                     if (S[a] != (uint16_t)L[i + 16 + 2 * k] || S[b] != (uint16_t)L[i + 17 + 2 * k]) {
                         printf("slicer address wrong: i %d bit %d\n", i, k);
