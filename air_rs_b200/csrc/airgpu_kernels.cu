@@ -41,6 +41,10 @@ namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+#ifndef AIRGPU_STAGE_DEFAULT
+#define AIRGPU_STAGE_DEFAULT 0      // 1: TMA-staged U8 kernel on aligned single-segment captures (A/B: DESIGN.md section 5)
+#endif
+
 // ---- CRC-24 single-bit syndromes -------------------------------------------
 // Frame bit p (MSB first, p = 0..111) has weight x^(111-p) in (data * x^24 + parity),
 // so its syndrome is x^(111-p) mod 0x1FFF409.  For p >= 88 that is the parity bit
@@ -112,19 +116,47 @@ __device__ __forceinline__ void levels_u8_streams(uint32_t wa, uint32_t wb, uint
     // 16 bits with multiplies, +2 FMA-pipe instructions per call -- was slower: 4.66 vs 4.36 ms)
 }
 
-// CS16: one 32-bit word = (re, im) little-endian i16.  Returns 65535 - floor(sqrt(re^2+im^2)), exactly.
-// MUFU gives sqrt to ~1e-2 absolute at this range (n <= 2^31); biasing it down by 0.02 makes the
-// truncated value r either the answer or one below it, so a single test of (r+1)^2 <= n finishes.
-__device__ __forceinline__ uint32_t level_cs16(uint32_t w)
+// CS16: one 32-bit word = (re, im) little-endian i16.  Returns -floor(sqrt(re^2+im^2)) (mod 2^32), exactly;
+// the level is 0xFFFF + that.
+//   n = re^2 + im^2 <= 2^31.  MUFU sqrt of float(n) is within a relative 2^-21 of the true root s; scaled UP by
+//   (1 + 2^-20) it lies in [s, s + 1), so its integer part r is isqrt(n) or isqrt(n) + 1, and the sign of
+//   n - r^2 (|n - r^2| < 2^17: no wrap-around) says which.
+// Instruction budget (tools/ubench3.cu: F2I, I2F.S16, POPC share the 16-lane XU pipe with MUFU; ISETP, SEL, LOP3
+// the 16-lane integer pipe): the integer part is taken with one FFMA.RZ against 2^23 (the sum's ulp is 1, so
+// round-toward-zero IS the floor) instead of FADD + F2I, and the fix-up is IMADs plus one shift instead of
+// IMAD + ISETP + SEL.  `one` / `minus_one` are kernel parameters so that ptxas keeps the additions on the FMA pipe.
+__device__ __forceinline__ uint32_t neg_isqrt_cs16(uint32_t w, uint32_t minus_one, uint32_t one)
 {
-    const int re = (int)(short)(unsigned short)w;       // sign-extended low half
-    const int im = ((int)w) >> 16;
-    const uint32_t n = (uint32_t)(re * re) + (uint32_t)(im * im);
-    float f;
+    // n = re^2 + im^2 without unpacking: a 16-bit value is lowbyte (unsigned) + 256 * highbyte (signed), so with
+    // bp = (re.lo, im.lo, re.hi, im.hi) two 16 x 8-bit dot products give (re, im).(re.lo, im.lo) and
+    // (re, im).(re.hi, im.hi): one PRMT on the integer pipe, the rest on the FMA pipe
+    const uint32_t bp = __byte_perm(w, 0u, 0x3120);
+    int hi, lo;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(w), "r"(bp), "r"(0));
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(w), "r"(bp), "r"(hi * 256));
+    const uint32_t n = (uint32_t)lo;
+    float f, t;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(__uint2float_rz(n)));
-    const uint32_t r = __float2uint_rz(f - 0.02f);      // negative -> 0
-    const uint32_t up = r * (r + 2u) + 1u;              // (r+1)^2 <= 46342^2 < 2^32
-    return (0xFFFFu - r) - (up <= n ? 1u : 0u);
+    asm("fma.rz.f32 %0, %1, %2, %3;" : "=f"(t) : "f"(f), "f"(1.00000095367431640625f), "f"(8388608.0f));
+    const uint32_t q = __float_as_uint(t);                       // 0x4B000000 + r
+    uint32_t r, nr, d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(q), "r"(one), "r"(0xB5000000u));          // q - 0x4B000000
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nr) : "r"(q), "r"(minus_one), "r"(0x4B000000u));   // -r
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(r), "r"(nr), "r"(n));                     // n - r^2
+    uint32_t u;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(d >> 31), "r"(one), "r"(nr));             // -(r - [n < r^2])
+    return u;
+}
+
+// two samples of the two streams -> one word (level of stream 0 | level of stream 1 << 16), level = 0xFFFF - isqrt
+__device__ __forceinline__ uint32_t level_word_cs16(uint32_t wa, uint32_t wb, uint32_t minus_one, uint32_t one)
+{
+    const uint32_t ua = neg_isqrt_cs16(wa, minus_one, one), ub = neg_isqrt_cs16(wb, minus_one, one);
+    // (0xFFFF + ua) + ((0xFFFF + ub) << 16) = ua + (ub << 16) - 1  (mod 2^32)
+    uint32_t v;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(v) : "r"(ub), "r"(65536u), "r"(ua));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(v) : "r"(v), "r"(one), "r"(minus_one));
+    return v;
 }
 
 // Eight words of the tile from eight samples of each stream.
@@ -138,14 +170,15 @@ __device__ __forceinline__ void words_of_chunk8(uint4 a0, uint4 a1, uint4 b0, ui
         levels_u8_streams(a0.z, b0.z, minus_one, o1.x, o1.y);
         levels_u8_streams(a0.w, b0.w, minus_one, o1.z, o1.w);
     } else {
-        o0.x = level_cs16(a0.x) | (level_cs16(b0.x) << 16);
-        o0.y = level_cs16(a0.y) | (level_cs16(b0.y) << 16);
-        o0.z = level_cs16(a0.z) | (level_cs16(b0.z) << 16);
-        o0.w = level_cs16(a0.w) | (level_cs16(b0.w) << 16);
-        o1.x = level_cs16(a1.x) | (level_cs16(b1.x) << 16);
-        o1.y = level_cs16(a1.y) | (level_cs16(b1.y) << 16);
-        o1.z = level_cs16(a1.z) | (level_cs16(b1.z) << 16);
-        o1.w = level_cs16(a1.w) | (level_cs16(b1.w) << 16);
+        const uint32_t one = 0u - minus_one;
+        o0.x = level_word_cs16(a0.x, b0.x, minus_one, one);
+        o0.y = level_word_cs16(a0.y, b0.y, minus_one, one);
+        o0.z = level_word_cs16(a0.z, b0.z, minus_one, one);
+        o0.w = level_word_cs16(a0.w, b0.w, minus_one, one);
+        o1.x = level_word_cs16(a1.x, b1.x, minus_one, one);
+        o1.y = level_word_cs16(a1.y, b1.y, minus_one, one);
+        o1.z = level_word_cs16(a1.z, b1.z, minus_one, one);
+        o1.w = level_word_cs16(a1.w, b1.w, minus_one, one);
     }
 }
 
@@ -380,21 +413,27 @@ __device__ __noinline__ unsigned long long scan_tile_ordered(const uint16_t *lv,
     return ((unsigned long long)sink.gate << 32) | sink.seq;
 }
 
-// One tile = kWarpTile candidate offsets, done by one warp in its private slice of shared memory.
+// ---- one tile = kWarpTile candidate offsets, done by one warp in its private slice of shared memory ----
+
+// Geometry of a tile.  `rem` = samples from this warp's first sample to the end of its segment;
+// everything else follows from it.  All tile starts are multiples of 2048 samples, so 16-byte
+// alignment of the loads is a per-launch property (p.vec_ok, computed by the host).  Tiles below
+// p.full_tiles (single-segment launches: all but the last two) are complete and need none of the
+// 64-bit arithmetic.
+struct TileGeom {
+    const uint8_t *src;          // first sample of the tile
+    unsigned long long rem;      // samples to the end of the segment
+    int wcands;                  // candidate offsets of this tile: min(kWarpTile, rem - 240)
+};
+
 template <int FMT, bool kSingleSegment>
-__device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigned tile, const int lane, uint16_t *lv)
+__device__ __forceinline__ TileGeom tile_geometry(const DecodeParams &p, const unsigned tile)
 {
     constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
-    constexpr int kChunkBytes = 8 * BPS;
-
-    // Geometry.  `rem` = samples from this warp's first sample to the end of its segment;
-    // everything else follows from it.  All tile starts are multiples of 2048 samples, so
-    // 16-byte alignment of the loads is a per-launch property (p.vec_ok, computed by the host).
-    // Tiles below p.full_tiles (single-segment launches: all but the last two) are complete and
-    // need none of the 64-bit arithmetic.
     unsigned long long seg_start = 0, wpos = (unsigned long long)tile * kWarpTile;
-    unsigned long long rem = (unsigned long long)(kStream + kTileWords);
-    int wcands = kWarpTile;
+    TileGeom g;
+    g.rem = (unsigned long long)(kStream + kTileWords);
+    g.wcands = kWarpTile;
     if (!kSingleSegment || tile >= p.full_tiles) {
         unsigned seg = 0, tile_in_seg = tile;
         if (!kSingleSegment) {
@@ -404,48 +443,45 @@ __device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigne
         seg_start = kSingleSegment ? 0ull : (unsigned long long)seg * p.seg_len;
         const unsigned long long seg_n = kSingleSegment ? p.n_samples : min(p.seg_len, p.n_samples - seg_start);
         wpos = (unsigned long long)tile_in_seg * kWarpTile;
-        rem = seg_n > wpos ? seg_n - wpos : 0ull;
-        wcands = rem > (unsigned long long)kFrameSamples
-                     ? (int)min((unsigned long long)kWarpTile, rem - kFrameSamples) : 0;
+        g.rem = seg_n > wpos ? seg_n - wpos : 0ull;
+        g.wcands = g.rem > (unsigned long long)kFrameSamples
+                       ? (int)min((unsigned long long)kWarpTile, g.rem - kFrameSamples) : 0;
     }
-    if (wcands == 0) {
-        if (lane == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
-        return;
-    }
-    uint4 *scratch = reinterpret_cast<uint4 *>(p.scratch);
-    Sink sink;
-    sink.slots = scratch + (unsigned long long)tile * (kSlotsPerTile * 2);
-    sink.overflow = nullptr;
-    sink.ovf_room = 0;
-    sink.seq = 0;
-    sink.gate = 0;
+    g.src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
+    return g;
+}
 
-    // ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
-    // Unit of work: 8 words of the tile = 8 samples of stream 0 (tile samples 8c ..) and 8 samples
-    // of stream 1 (1024 + 8c ..).  Words 1024 .. 1263 repeat, in their low halves, levels that
-    // words 0 .. 239 hold in their high halves: those loads hit L2.
-    const uint8_t *src = static_cast<const uint8_t *>(p.iq) + (seg_start + wpos) * BPS;
-    constexpr int kRounds = (kTileChunks8 + 31) / 32;           // 5; the last round has 30 units
+constexpr int kRounds = (kTileChunks8 + 31) / 32;           // 5 rounds of 32 units; the last has 30
+
+// ---- phase 1: IQ -> inverted levels in the warp's shared-memory slice ----
+// Unit of work: 8 words of the tile = 8 samples of stream 0 (tile samples 8c ..) and 8 samples
+// of stream 1 (1024 + 8c ..).  Words 1024 .. 1263 repeat, in their low halves, levels that
+// words 0 .. 239 hold in their high halves: those loads hit L2.
+template <int FMT>
+__device__ __forceinline__ void load_levels(const DecodeParams &p, const TileGeom &g, const int lane, uint16_t *lv)
+{
+    constexpr int BPS = (FMT == AIRGPU_FMT_U8) ? 2 : 4;
+    constexpr int kChunkBytes = 8 * BPS;
     constexpr int kStreamBytes = kStream * BPS;
-    if (p.vec_ok && rem >= (unsigned long long)(kStream + kTileWords)) {
+    const uint8_t *src = g.src;
+    if (p.vec_ok && g.rem >= (unsigned long long)(kStream + kTileWords)) {
         // unit c = lane + 32 m: global address and shared address are both "per-lane base +
         // compile-time offset" (padded 16-byte chunks 2c + (c >> 2) = 2 lane + (lane >> 2) + 72 m)
         const uint8_t *gsrc = src + lane * kChunkBytes;
         uint4 *sdst = reinterpret_cast<uint4 *>(lv) + (2 * lane + (lane >> 2));
         if (FMT == AIRGPU_FMT_CS16) {
             // rolled (fully unrolled it is far too much code for the instruction cache)
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             uint4 a0 = ldg_stream(gsrc), a1 = ldg_stream(gsrc + 16);
             uint4 b0 = ldg_stream(gsrc + kStreamBytes), b1 = ldg_stream(gsrc + kStreamBytes + 16);
 #pragma unroll 1
             for (int m = 0; m < kRounds; ++m) {
-                uint4 na0 = z, na1 = z, nb0 = z, nb1 = z;
+                uint4 na0 = a0, na1 = a1, nb0 = b0, nb1 = b1;      // (never converted when not reloaded)
                 if (m + 1 < kRounds && lane + 32 * (m + 1) < kTileChunks8) {
-                    const uint8_t *g = gsrc + 32 * (m + 1) * kChunkBytes;
-                    na0 = ldg_stream(g);
-                    na1 = ldg_stream(g + 16);
-                    nb0 = ldg_stream(g + kStreamBytes);
-                    nb1 = ldg_stream(g + kStreamBytes + 16);
+                    const uint8_t *gn = gsrc + 32 * (m + 1) * kChunkBytes;
+                    na0 = ldg_stream(gn);
+                    na1 = ldg_stream(gn + 16);
+                    nb0 = ldg_stream(gn + kStreamBytes);
+                    nb1 = ldg_stream(gn + kStreamBytes + 16);
                 }
                 if (lane + 32 * m < kTileChunks8) {
                     uint4 o0, o1;
@@ -481,7 +517,7 @@ __device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigne
         }
     } else {
         // edge of a segment or an unaligned buffer: same arithmetic, guarded byte loads
-        const long long avail = (long long)rem * BPS;   // bytes to the end of the segment
+        const long long avail = (long long)g.rem * BPS;   // bytes to the end of the segment
 #pragma unroll 1
         for (int c = lane; c < kTileChunks8; c += 32) {
             const long long oa = (long long)c * kChunkBytes, ob = oa + kStreamBytes;
@@ -497,9 +533,20 @@ __device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigne
             d[1] = o1;
         }
     }
-    __syncwarp();
+}
 
-    // ---- phase 2+3: gate, slice, CRC; frames go straight to the tile's scratch slots ----
+// ---- phase 2..4: gate, slice, CRC; frames go straight to the tile's scratch slots; publish the count ----
+template <int FMT>
+__device__ __forceinline__ void finish_tile(const DecodeParams &p, const unsigned tile, const int wcands, const int lane,
+                                            const uint16_t *lv)
+{
+    uint4 *scratch = reinterpret_cast<uint4 *>(p.scratch);
+    Sink sink;
+    sink.slots = scratch + (unsigned long long)tile * (kSlotsPerTile * 2);
+    sink.overflow = nullptr;
+    sink.ovf_room = 0;
+    sink.seq = 0;
+    sink.gate = 0;
     uint32_t nvalid, gate;
     if (!p.force_ordered) {
         scan_tile_fast<FMT>(lv, wcands, lane, p.minus_one, sink);
@@ -510,8 +557,6 @@ __device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigne
         nvalid = (uint32_t)r;
         gate = (uint32_t)(r >> 32);
     }
-
-    // ---- phase 4: publish the tile's count ----
     unsigned long long ovf_base = 0;
     if (nvalid > (uint32_t)kSlotsPerTile) {
         // rare (degenerate input): redo the range in ascending offset order; frames kSlotsPerTile..
@@ -527,6 +572,19 @@ __device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigne
         // per-group sums, gate passes << 32 | frames: one fire-and-forget RED (no atomic with a return value)
         if (gate) atomicAdd(&p.group_sum[tile / kGroupTiles], ((unsigned long long)gate << 32) | nvalid);
     }
+}
+
+template <int FMT, bool kSingleSegment>
+__device__ __forceinline__ void decode_tile(const DecodeParams &p, const unsigned tile, const int lane, uint16_t *lv)
+{
+    const TileGeom g = tile_geometry<FMT, kSingleSegment>(p, tile);
+    if (g.wcands == 0) {
+        if (lane == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
+        return;
+    }
+    load_levels<FMT>(p, g, lane, lv);
+    __syncwarp();
+    finish_tile<FMT>(p, tile, g.wcands, lane, lv);
 }
 
 #ifndef AIRGPU_MIN_CTAS
@@ -558,6 +616,106 @@ decode_kernel(const DecodeParams p)
         if (tile >= min(p.n_tiles, (cta + 1) * (kWarps * p.tiles_per_warp))) break;
         decode_tile<FMT, kSingleSegment>(p, tile, lane, s_lvl[warp]);
         tile += kWarps;
+        __syncwarp();    // every lane is done reading the slice before the next tile overwrites it
+    }
+}
+
+// ---- A/B variant (AIRGPU_STAGE=1): the same path with the raw IQ of a warp's NEXT tile staged in
+// shared memory by the TMA unit (1-D cp.async.bulk completing on an mbarrier) while the warp runs
+// the gate and the survivor path of the current one.  The 2288 samples a tile reads are one
+// contiguous 4576-byte range (U8), so one bulk copy per tile, issued by lane 0, replaces the ten
+// LDG.128 per lane and their forty registers; the price is 4.6 KB more shared memory per warp
+// (5 CTAs = 20 warps per SM instead of 32).  U8, single segment, aligned buffers only; every
+// other launch and the ragged last tiles take the loader above.  Measured: DESIGN.md section 5.
+constexpr int kRawBytesU8 = (kStream + kTileWords) * 2;      // 4576: a multiple of 16
+constexpr int kRawPitch = 4608;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_issue(uint32_t dst, const void *src, uint32_t bar)
+{
+    // generic-proxy reads of the buffer (phase 1 of the previous tile) are ordered before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kRawBytesU8) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"((uint32_t)kRawBytesU8), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void stage_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+#ifndef AIRGPU_STAGED_MIN_CTAS
+#define AIRGPU_STAGED_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(kThreads, AIRGPU_STAGED_MIN_CTAS)
+decode_kernel_staged_u8(const DecodeParams p)
+{
+    constexpr int FMT = AIRGPU_FMT_U8;
+    __shared__ __align__(128) uint16_t s_lvl[kWarps][2 * kTileWordsPadded];
+    __shared__ __align__(128) uint8_t s_raw[kWarps][kRawPitch];
+    __shared__ __align__(8) unsigned long long s_bar[kWarps];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint16_t *lv = s_lvl[warp];
+    const uint32_t raw = smem_u32(s_raw[warp]), bar = smem_u32(&s_bar[warp]);
+    unsigned tile = blockIdx.x * (kWarps * p.tiles_per_warp) + warp;
+    const unsigned bound = min(p.n_tiles, (blockIdx.x + 1) * (kWarps * p.tiles_per_warp));
+    if (tile >= bound) return;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // complete tiles (tile < p.full_tiles) are staged; the launcher guarantees p.vec_ok
+    bool staged = tile < p.full_tiles;
+    if (staged && lane == 0) stage_issue(raw, static_cast<const uint8_t *>(p.iq) + (unsigned long long)tile * (kWarpTile * 2), bar);
+    uint32_t parity = 0;
+#pragma unroll 1
+    for (; tile < bound; tile += kWarps) {
+        const unsigned next = tile + kWarps;
+        const bool next_staged = next < bound && next < p.full_tiles;
+        int wcands = kWarpTile;
+        if (staged) {
+            stage_wait(bar, parity);
+            parity ^= 1u;
+            // unit c = lane + 32 m reads 16 bytes of each stream from the staged tile (consecutive lanes,
+            // consecutive 16-byte chunks: conflict free) and stores its two chunks of words as the loader does
+            const uint4 *rsrc = reinterpret_cast<const uint4 *>(s_raw[warp]) + lane;
+            uint4 *sdst = reinterpret_cast<uint4 *>(lv) + (2 * lane + (lane >> 2));
+#pragma unroll
+            for (int m = 0; m < kRounds; ++m) {
+                if (32 * m + 31 < kTileChunks8 || lane + 32 * m < kTileChunks8) {
+                    const uint4 a = rsrc[32 * m], b = rsrc[32 * m + kStream * 2 / 16];
+                    uint4 o0, o1;
+                    words_of_chunk8<FMT>(a, a, b, b, p.minus_one, o0, o1);
+                    sdst[72 * m] = o0;
+                    sdst[72 * m + 1] = o1;
+                }
+            }
+            __syncwarp();      // every lane has read the staged bytes and written its words
+        } else {
+            const TileGeom g = tile_geometry<FMT, true>(p, tile);
+            wcands = g.wcands;
+            if (wcands) load_levels<FMT>(p, g, lane, lv);
+            __syncwarp();
+        }
+        // the staging buffer is free again: the next tile's bytes arrive during the gate and the survivor path
+        if (next_staged && lane == 0)
+            stage_issue(raw, static_cast<const uint8_t *>(p.iq) + (unsigned long long)next * (kWarpTile * 2), bar);
+        if (wcands == 0) {
+            if (lane == 0) p.tile_tab[tile] = make_uint2(0u, 0u);
+        } else {
+            finish_tile<FMT>(p, tile, wcands, lane, lv);
+        }
+        staged = next_staged;
         __syncwarp();    // every lane is done reading the slice before the next tile overwrites it
     }
 }
@@ -757,10 +915,16 @@ __global__ void levels_u8_kernel(uint16_t *out, uint32_t minus_one)
     out[idx] = same ? (uint16_t)v : (uint16_t)0xFFFFu;
 }
 
-__global__ void levels_cs16_kernel(const uint32_t *iq, unsigned long long n, uint16_t *out)
+__global__ void levels_cs16_kernel(const uint32_t *iq, unsigned long long n, uint16_t *out, uint32_t minus_one)
 {
     unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < n) out[idx] = (uint16_t)level_cs16(iq[idx]);
+    if (idx >= n) return;
+    // the decode kernel's own arithmetic: both halves of a packed word must agree with the single-sample form
+    const uint32_t w = iq[idx], other = iq[(idx * 7 + 3) % n];
+    const uint32_t one = 0u - minus_one;
+    const uint32_t v = level_word_cs16(w, other, minus_one, one), x = level_word_cs16(other, w, minus_one, one);
+    const uint32_t lvl = 0xFFFFu + neg_isqrt_cs16(w, minus_one, one);
+    out[idx] = ((v & 0xFFFFu) == lvl && (x >> 16) == lvl && lvl <= 0xFFFFu) ? (uint16_t)lvl : (uint16_t)0u;
 }
 
 }  // namespace
@@ -783,8 +947,13 @@ cudaError_t launch_decode(int format, const DecodeParams &params, cudaStream_t s
     p.tiles_per_warp = forced > 0 ? (unsigned)forced : (p.n_tiles >= 131072u ? 4u : (p.n_tiles >= 32768u ? 2u : 1u));
     const unsigned per_cta = kWarps * p.tiles_per_warp;
     const unsigned grid = (p.n_tiles + per_cta - 1) / per_cta;
+    static const int stage = [] {
+        const char *e = std::getenv("AIRGPU_STAGE");
+        return e ? std::atoi(e) : AIRGPU_STAGE_DEFAULT;
+    }();
     if (format == AIRGPU_FMT_U8) {
-        if (single) decode_kernel<AIRGPU_FMT_U8, true><<<grid, kThreads, 0, stream>>>(p);
+        if (single && stage && p.vec_ok && p.full_tiles) decode_kernel_staged_u8<<<grid, kThreads, 0, stream>>>(p);
+        else if (single) decode_kernel<AIRGPU_FMT_U8, true><<<grid, kThreads, 0, stream>>>(p);
         else decode_kernel<AIRGPU_FMT_U8, false><<<grid, kThreads, 0, stream>>>(p);
     } else {
         if (single) decode_kernel<AIRGPU_FMT_CS16, true><<<grid, kThreads, 0, stream>>>(p);
@@ -824,7 +993,7 @@ cudaError_t launch_levels_u8(uint16_t *out65536, cudaStream_t stream)
 cudaError_t launch_levels_cs16(const int16_t *iq, unsigned long long n, uint16_t *out, cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;
-    levels_cs16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint32_t *>(iq), n, out);
+    levels_cs16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint32_t *>(iq), n, out, 0xFFFFFFFFu);
     return cudaGetLastError();
 }
 

@@ -38,7 +38,16 @@ namespace packed {
 #if defined(__CUDA_ARCH__)
 AIRGPU_HD uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 AIRGPU_HD uint32_t max2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+#if defined(AIRGPU_GATE_2IN)
+AIRGPU_HD uint32_t min3(uint32_t a, uint32_t b, uint32_t c)   // A/B: tools/ubench4.cu (the empty asm keeps ptxas from re-fusing)
+{
+    uint32_t t = __vminu2(a, b);
+    asm volatile("" : "+r"(t));
+    return __vminu2(t, c);
+}
+#else
 AIRGPU_HD uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+#endif
 AIRGPU_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 // 1 in every half where hi > lo, any 16-bit levels: max - lo is non-zero exactly there (no borrow
 // between the halves because max >= lo in each), clamped to 1.  The subtraction is written as

@@ -275,6 +275,8 @@ def run_ours(args):
     # ---- end to end: host (pinned) buffers through airgpu_decode, H2D + D2H inside the timed region
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         h_iq = torch.empty(2 * n_local, dtype=torch.uint8, pin_memory=True)
         h_iq.copy_(iq)
         torch.cuda.synchronize()
@@ -425,6 +427,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (kernel A/B runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

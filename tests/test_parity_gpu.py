@@ -467,6 +467,46 @@ print("ok")
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_tma_staged_variant(tmp_path):
+    """AIRGPU_STAGE=1 selects decode_kernel_staged_u8 (raw IQ of the next tile staged in shared memory by a 1-D
+    bulk copy on an mbarrier) for aligned single-segment U8 captures: same records, same gate-pass counter --
+    one tile per warp and three (staging pipeline across tiles), captures that end in ragged tiles, a constant
+    run that overflows the fixed slots, an unaligned buffer (falls back to the loader)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, "tests")
+import numpy as np
+from air_rs_b200.decoder import AdsbDecoder
+from air_rs_b200.native import FMT_U8
+from oracle import oracle_c
+from common import capture_u8, frames_equal, describe_diff
+_, big = capture_u8(seed=79, n=1_000_003 + 8, df17=4000.0)
+big[2 * 300_000: 2 * 300_400] = 31          # 160 frames at consecutive offsets
+with AdsbDecoder(fmt=FMT_U8, max_buffer_samples=1 << 20, max_frames=1 << 16) as d:
+    for n in (1_000_003, 500_000, 2048 * 40 + 240, 2048 * 40 + 239, 2288, 2289, 4096 + 2288, 70_000):
+        for shift in (0, 1):                   # shift 1: the buffer starts 2 bytes off 16-byte alignment
+            iq = np.ascontiguousarray(big[2 * shift: 2 * (shift + n)])
+            if shift:
+                pad = np.zeros(2 * n + 16, dtype=np.uint8)
+                base = (-pad.ctypes.data) % 16 + 2
+                pad[base: base + 2 * n] = iq
+                iq = pad[base: base + 2 * n]
+            got = d.decode(iq)
+            want, wgp = oracle_c.decode_fast(iq, 0, 0, threads=4)
+            assert frames_equal(got, want), (n, shift, describe_diff(got, want))
+            assert d.stats()["gate_passes"] == wgp
+print("ok")
+'''
+    root = Path(__file__).resolve().parents[1]
+    for tpw in ("1", "3"):
+        env = dict(os.environ, AIRGPU_STAGE="1", AIRGPU_TILES_PER_WARP=tpw)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_several_tiles_per_warp(tmp_path):
     """Long captures make a warp decode several tiles in a row (launch_decode picks 2 or 4 from 67 M samples
     up).  Force 3 on small inputs -- a tile count that is not a multiple of 12, both formats, independent
