@@ -45,6 +45,12 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 #define AIRGPU_STAGE_DEFAULT 0      // 1: TMA-staged U8 kernel on aligned single-segment captures (A/B: DESIGN.md section 5)
 #endif
 
+// One store to an NVSwitch multicast address: the switch writes it to the same offset of every rank's mapping.
+__device__ __forceinline__ void multimem_st_u64(unsigned long long *mc, unsigned long long v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(mc), "l"(v) : "memory");
+}
+
 // ---- CRC-24 single-bit syndromes -------------------------------------------
 // Frame bit p (MSB first, p = 0..111) has weight x^(111-p) in (data * x^24 + parity),
 // so its syndrome is x^(111-p) mod 0x1FFF409.  For p >= 88 that is the parity bit
@@ -759,7 +765,7 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 
 __global__ void __launch_bounds__(kScanThreads, 1)
 group_scan_kernel(const unsigned long long *group_sum, unsigned n_groups, unsigned long long *group_base,
-                  unsigned long long *d_total, unsigned long long *d_gate)
+                  unsigned long long *d_total, unsigned long long *d_gate, const OutSet dst)
 {
     __shared__ unsigned long long s_warp[33];
     unsigned long long running = *d_total;   // frames already in `out` (pieces of one call append)
@@ -778,25 +784,49 @@ group_scan_kernel(const unsigned long long *group_sum, unsigned n_groups, unsign
     if (threadIdx.x == 0) {
         *d_total = running;
         *d_gate += gate;                     // gate passes accumulate over the pieces of a call
+        // frame exchange: the count travels with the records (peer-mapped or multicast addresses)
+        if (dst.multicast) {
+            if (dst.count[0]) multimem_st_u64(dst.count[0], running);
+        } else {
+            for (unsigned j = 0; j < dst.n; ++j)
+                if (dst.count[j] && dst.count[j] != d_total) *dst.count[j] = running;
+        }
     }
 }
 
 // Scratch slot -> airgpu_frame (three little-endian u64 words): byte-swapped frame words, then
 // bytes 12, 13 | fixed_bit | reserved, then the absolute sample offset.
-__device__ __forceinline__ void store_record(unsigned long long *out, unsigned long long dst, const uint4 q, uint32_t meta,
+// kMode 0: one destination (plain decode); 1: dst.n destinations, plain stores to local / peer-mapped memory (the
+// frame exchange over NVLink, fused: no copy engine, no second kernel); 2: one multimem.st per word to an NVSwitch
+// multicast address -- the switch replicates it to every rank, so a rank's NVLink egress is 1x its list, not (n-1)x.
+template <int kMode>
+__device__ __forceinline__ void store_record(const OutSet &o, unsigned long long dst, const uint4 q, uint32_t meta,
                                              unsigned long long tile_off0)
 {
     const unsigned long long w0 = (unsigned long long)__byte_perm(q.x, 0, 0x0123) |
                                   ((unsigned long long)__byte_perm(q.y, 0, 0x0123) << 32);
     const uint32_t hi = __byte_perm(q.w, meta >> 16, 0x7423);
     const unsigned long long w1 = (unsigned long long)__byte_perm(q.z, 0, 0x0123) | ((unsigned long long)hi << 32);
-    out[dst * 3 + 0] = w0;
-    out[dst * 3 + 1] = w1;
-    out[dst * 3 + 2] = tile_off0 + (meta & 0xFFFFu);
+    const unsigned long long w2 = tile_off0 + (meta & 0xFFFFu);
+    if (kMode == 2) {
+        unsigned long long *out = o.out[0] + dst * 3;
+        multimem_st_u64(out, w0);
+        multimem_st_u64(out + 1, w1);
+        multimem_st_u64(out + 2, w2);
+    } else {
+#pragma unroll 1
+        for (unsigned j = 0; j < (kMode == 0 ? 1u : o.n); ++j) {
+            unsigned long long *out = o.out[j] + dst * 3;
+            out[0] = w0;
+            out[1] = w1;
+            out[2] = w2;
+        }
+    }
 }
 
+template <int kMode>
 __global__ void __launch_bounds__(kGroupTiles)
-gather_kernel(const DecodeParams p, const unsigned long long *group_base, unsigned long long *out)
+gather_kernel(const DecodeParams p, const unsigned long long *group_base, const OutSet out)
 {
     // One CTA per group of kGroupTiles tiles: scan the counts in shared memory, then one
     // THREAD per record of the group (binary search for its tile) so that all record copies of
@@ -854,7 +884,7 @@ gather_kernel(const DecodeParams p, const unsigned long long *group_base, unsign
         const unsigned seg = tile / p.tiles_per_seg;
         const unsigned long long off0 = p.base_offset + (unsigned long long)seg * p.seg_len +
                                         (unsigned long long)(tile - seg * p.tiles_per_seg) * kWarpTile;
-        store_record(out, dst, q, meta, off0);
+        store_record<kMode>(out, dst, q, meta, off0);
     }
 }
 
@@ -962,16 +992,42 @@ cudaError_t launch_decode(int format, const DecodeParams &params, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned long long *d_total,
-                            cudaStream_t stream)
+cudaError_t launch_finalize(const DecodeParams &p, const OutSet &dst, unsigned long long *d_total, cudaStream_t stream)
 {
     const unsigned n_groups = (p.n_tiles + kGroupTiles - 1) / kGroupTiles;
     group_scan_kernel<<<1, kScanThreads, 0, stream>>>(p.group_sum, n_groups, p.group_base, d_total,
-                                                       p.counters + kCounterGate);
+                                                       p.counters + kCounterGate, dst);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (n_groups == 0) return cudaSuccess;
-    gather_kernel<<<n_groups, kGroupTiles, 0, stream>>>(p, p.group_base, reinterpret_cast<unsigned long long *>(out));
+    if (dst.multicast) gather_kernel<2><<<n_groups, kGroupTiles, 0, stream>>>(p, p.group_base, dst);
+    else if (dst.n > 1) gather_kernel<1><<<n_groups, kGroupTiles, 0, stream>>>(p, p.group_base, dst);
+    else gather_kernel<0><<<n_groups, kGroupTiles, 0, stream>>>(p, p.group_base, dst);
+    return cudaGetLastError();
+}
+
+// One-kernel barrier between the ranks of an exchange.  Thread q publishes this rank's epoch in rank q's flag
+// array (flags[q][rank], peer-mapped) with release semantics at system scope -- everything this GPU stored
+// before (the records of the gather kernels earlier in the stream) is visible to a peer that acquires it -- and
+// then waits until rank q's epoch shows up in its own array (flags[rank][q]).  Every rank runs on its own GPU
+// (never two ranks of one exchange on one device: they would wait for each other's kernel).
+__global__ void peer_barrier_kernel(const PeerFlags f)
+{
+    const unsigned q = threadIdx.x;
+    if (q >= f.n_ranks) return;
+    __threadfence_system();
+    unsigned long long *theirs = f.flags[q] + f.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(f.epoch) : "memory");
+    const unsigned long long *mine = f.flags[f.rank] + q;
+    unsigned long long seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    } while (seen < f.epoch);
+}
+
+cudaError_t launch_peer_barrier(const PeerFlags &f, cudaStream_t stream)
+{
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(f);
     return cudaGetLastError();
 }
 

@@ -49,11 +49,26 @@ struct DecodeParams {
 
 enum { kCounterGate = 1, kNumCounters = 4 };
 
+// Where the ordered records and the frame count of a call go: one local array, or the same offset of several
+// local / peer-mapped arrays, or one NVSwitch multicast address (airgpu_decode_device_peers).
+struct OutSet {
+    unsigned long long *out[AIRGPU_MAX_PEERS];     // airgpu_frame arrays, u64 view
+    unsigned long long *count[AIRGPU_MAX_PEERS];   // where the count lands (may be nullptr)
+    unsigned n;
+    unsigned multicast;
+};
+
+struct PeerFlags {
+    unsigned long long *flags[AIRGPU_MAX_PEERS];   // flags[q]: rank q's array of n_ranks epochs, as mapped on this device
+    unsigned n_ranks, rank;
+    unsigned long long epoch;
+};
+
 // Launchers (stream-ordered, no synchronisation inside).
 cudaError_t launch_decode(int format, const DecodeParams &p, cudaStream_t stream);
 // Ordered frames are appended to `out` at index *d_total (device counter, updated in place).
-cudaError_t launch_finalize(const DecodeParams &p, airgpu_frame *out, unsigned long long *d_total,
-                            cudaStream_t stream);
+cudaError_t launch_finalize(const DecodeParams &p, const OutSet &dst, unsigned long long *d_total, cudaStream_t stream);
+cudaError_t launch_peer_barrier(const PeerFlags &f, cudaStream_t stream);
 
 // N1: per-frame field decode (packet.rs:25-49, msgs.rs:69-102, 171-201).
 cudaError_t launch_decode_fields(const airgpu_frame *frames, unsigned long long n, airgpu_fields *out, cudaStream_t stream);

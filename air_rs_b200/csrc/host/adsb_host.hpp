@@ -162,11 +162,16 @@ inline uint64_t process_sdr_data_thread(Channel<IqBuffer> &rx, Channel<AdsbPacke
     auto drain = [&](size_t keep) {
         while (alive && pending.size() > keep) {
             size_t n = 0;
-            const int rc = airgpu_collect(ctx, pending.front(), out.data(), out.size(), &n);
+            int rc = airgpu_collect(ctx, pending.front(), out.data(), out.size(), &n);
+            if (rc == AIRGPU_ERR_OVERFLOW && n > out.size()) {
+                // more frames than the array holds (a constant buffer yields one at EVERY offset): the ticket is still
+                // collectable -- the reference sends every packet (adsb.rs:98-111), so nothing is dropped here either
+                out.resize(n);
+                rc = airgpu_collect(ctx, pending.front(), out.data(), out.size(), &n);
+            }
             pending.pop_front();
-            if (rc != AIRGPU_OK && rc != AIRGPU_ERR_OVERFLOW)
-                throw std::runtime_error(std::string("airgpu_collect: ") + airgpu_last_error());
-            for (size_t k = 0; k < std::min(n, out.size()); ++k) {
+            if (rc != AIRGPU_OK) throw std::runtime_error(std::string("airgpu_collect: ") + airgpu_last_error());
+            for (size_t k = 0; k < n; ++k) {
                 AdsbPacket pkt(std::vector<uint8_t>(out[k].bytes, out[k].bytes + 14));   // adsb.rs:107
                 if (!tx.send(std::move(pkt))) {
                     std::puts("Adsb msg receiver is dropped");                          // adsb.rs:108-111

@@ -80,10 +80,19 @@ class AdsbDecoder:
         return int(t.value)
 
     def collect(self, ticket: int) -> np.ndarray:
-        out = np.zeros(self.max_frames, dtype=FRAME_DTYPE)
-        n = C.c_size_t(0)
-        native.check(self._lib.airgpu_collect(self._h, ticket, out.ctypes.data, out.size, C.byref(n)))
-        return out[: n.value].copy()
+        """Frames of one submitted buffer.  Nothing is ever dropped: if the buffer yields more frames than
+        max_frames (a constant buffer yields one at every offset) the ticket stays collectable and is
+        collected again with room for all of them -- the reference sends every packet (adsb.rs:98-111)."""
+        cap = self.max_frames
+        while True:
+            out = np.zeros(cap, dtype=FRAME_DTYPE)
+            n = C.c_size_t(0)
+            rc = self._lib.airgpu_collect(self._h, ticket, out.ctypes.data, out.size, C.byref(n))
+            if rc == native.ERR_OVERFLOW and n.value > cap:
+                cap = int(n.value)
+                continue
+            native.check(rc)
+            return out[: n.value].copy()
 
     # -- one-shot, host memory ---------------------------------------------
     def decode(self, iq, segment_samples: int = 0, base_offset: int = 0, max_frames: Optional[int] = None,
@@ -112,6 +121,39 @@ class AdsbDecoder:
         """Asynchronous decode of device-resident IQ (raw pointers, see airgpu_decode_device)."""
         native.check(self._lib.airgpu_decode_device(self._h, d_iq, n_samples, segment_samples, base_offset, d_out,
                                                     cap, d_count or None, stream or None))
+
+    def decode_device_peers(self, d_iq: int, n_samples: int, outs, counts, cap: int, segment_samples: int = 0,
+                            base_offset: int = 0, stream: int = 0, multicast: bool = False) -> None:
+        """Asynchronous decode whose ordering kernels store every record and the frame count straight to each of
+        `outs` / `counts` (device-accessible addresses: local, peer-mapped, or ONE multicast address)."""
+        pe = native.Peers()
+        pe.struct_size = C.sizeof(native.Peers)
+        pe.n_outs = len(outs)
+        pe.multicast = 1 if multicast else 0
+        for j, (o, k) in enumerate(zip(outs, counts)):
+            pe.outs[j] = o
+            pe.counts[j] = k or None
+        native.check(self._lib.airgpu_decode_device_peers(self._h, d_iq, n_samples, segment_samples, base_offset,
+                                                          C.byref(pe), cap, stream or None))
+
+    def peer_barrier(self, flag_ptrs, rank: int, epoch: int, stream: int = 0) -> None:
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        native.check(self._lib.airgpu_peer_barrier(self._h, arr, len(flag_ptrs), rank, epoch, stream or None))
+
+    def reserve(self, n_samples: int, segment_samples: int = 0, cap: int = 0) -> None:
+        native.check(self._lib.airgpu_reserve(self._h, n_samples, segment_samples, cap))
+
+    def set_timing(self, enabled: bool) -> None:
+        native.check(self._lib.airgpu_set_timing(self._h, 1 if enabled else 0))
+
+    # -- CUDA graphs -----------------------------------------------------------
+    def graph_begin(self, stream: int) -> None:
+        native.check(self._lib.airgpu_graph_begin(self._h, stream))
+
+    def graph_end(self, stream: int) -> "Graph":
+        g = C.c_void_p()
+        native.check(self._lib.airgpu_graph_end(self._h, stream, C.byref(g)))
+        return Graph(g)
 
     def sync_count(self) -> int:
         n = C.c_uint64(0)
@@ -171,6 +213,74 @@ class AdsbDecoder:
         out = np.zeros(a.size // 2, dtype=np.uint16)
         native.check(self._lib.airgpu_dbg_levels_cs16(self._h, a.ctypes.data, out.size, out.ctypes.data))
         return out
+
+
+class Graph:
+    """airgpu_graph: a recorded sequence of device-side calls, replayed with one launch."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self._lib = native.lib()
+
+    def launch(self, stream: int) -> None:
+        native.check(self._lib.airgpu_graph_launch(self._h, stream))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.airgpu_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DecoderGroup:
+    """airgpu_group: one host thread, several GPUs (SURVEY 8(b) `airgpu_decode_sharded`)."""
+
+    def __init__(self, devices, fmt: int = FMT_CS16):
+        self._lib = native.lib()
+        self.fmt = fmt
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        native.check(self._lib.airgpu_group_create(arr, len(self.devices), fmt, C.byref(h)))
+        self._h = h
+
+    def decode(self, iq, base_offset: int = 0, max_frames: Optional[int] = None, n_samples: Optional[int] = None) -> np.ndarray:
+        if isinstance(iq, int):
+            ptr, n = iq, int(n_samples)
+        else:
+            a = _as_iq(iq, self.fmt)
+            ptr, n = a.ctypes.data, a.size // 2
+        cap = max_frames or max(4096, n // 256)
+        while True:
+            out = np.zeros(cap, dtype=FRAME_DTYPE)
+            got = C.c_size_t(0)
+            rc = self._lib.airgpu_group_decode(self._h, ptr, n, base_offset, out.ctypes.data, cap, C.byref(got))
+            if rc == native.ERR_OVERFLOW and max_frames is None:
+                cap = int(got.value)
+                continue
+            native.check(rc)
+            return out[: got.value].copy()
+
+    def stats(self):
+        arr = (native.Stats * len(self.devices))()
+        native.check(self._lib.airgpu_group_stats(self._h, arr, len(self.devices)))
+        return [{k: getattr(st, k) for k, _ in native.Stats._fields_} for st in arr]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.airgpu_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def host_alloc(nbytes: int) -> int:

@@ -67,6 +67,20 @@ class Stats(C.Structure):
 
 _vp, _sz, _u64 = C.c_void_p, C.c_size_t, C.c_uint64
 
+MAX_PEERS = 8
+
+
+class Peers(C.Structure):
+    """airgpu_peers: destinations of a fused frame exchange (device-accessible addresses)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("n_outs", C.c_uint32),
+        ("multicast", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("outs", _vp * MAX_PEERS),
+        ("counts", _vp * MAX_PEERS),
+    ]
+
 # every symbol include/airgpu.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "airgpu_version": (C.c_char_p, []),
@@ -80,6 +94,20 @@ SYMBOLS = {
     "airgpu_decode_device": (C.c_int, [_vp, _vp, _sz, _sz, _u64, _vp, _sz, _vp, _vp]),
     "airgpu_sync_count": (C.c_int, [_vp, C.POINTER(_u64)]),
     "airgpu_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "airgpu_playback_samples": (_sz, [_sz, _sz]),
+    "airgpu_reserve": (C.c_int, [_vp, _sz, _sz, _sz]),
+    "airgpu_set_timing": (C.c_int, [_vp, C.c_int]),
+    "airgpu_graph_begin": (C.c_int, [_vp, _vp]),
+    "airgpu_graph_end": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "airgpu_graph_launch": (C.c_int, [_vp, _vp]),
+    "airgpu_graph_destroy": (None, [_vp]),
+    "airgpu_decode_device_peers": (C.c_int, [_vp, _vp, _sz, _sz, _u64, C.POINTER(Peers), _sz, _vp]),
+    "airgpu_peer_barrier": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint32, C.c_uint32, _u64, _vp]),
+    "airgpu_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "airgpu_group_decode": (C.c_int, [_vp, _vp, _sz, _u64, _vp, _sz, C.POINTER(_sz)]),
+    "airgpu_group_stats": (C.c_int, [_vp, C.POINTER(Stats), C.c_uint32]),
+    "airgpu_group_destroy": (None, [_vp]),
+    "airgpu_decode_sharded": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.c_uint32, _vp, _sz, _u64, _vp, _sz, C.POINTER(_sz)]),
     "airgpu_decode_fields": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "airgpu_decode_fields_host": (C.c_int, [_vp, _vp, _sz, _vp]),
     "airgpu_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),

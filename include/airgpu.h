@@ -28,8 +28,12 @@
  *   whose CRC matches or is repairable -- there is NO skip after a hit and NO
  *   de-duplication (src/adsb.rs:113 is a no-op).  L < 240, which panics in the
  *   reference, yields zero frames here (the one deliberate deviation).
- *   segment_samples = 20000 reproduces the reference's playback chunking
+ *   segment_samples = 20000 reproduces the reference's playback CHUNKING
  *   (src/adsb.rs:78); one segment per received buffer reproduces the SDR path.
+ *   To reproduce a whole-file REPLAY pass only the samples the playback thread
+ *   sends: it loops `while i < data.len() - 20000` (src/adsb.rs:77), i.e. it
+ *   never sends the last chunk, complete or not -- n_samples =
+ *   ((len - 1) / 20000) * 20000 (airgpu_playback_samples() below).
  */
 #ifndef AIRGPU_H
 #define AIRGPU_H
@@ -41,7 +45,8 @@
 extern "C" {
 #endif
 
-#define AIRGPU_ABI_VERSION 1
+#define AIRGPU_ABI_VERSION 2
+#define AIRGPU_MAX_PEERS 8       /* destinations of a fused frame exchange: the GPUs of one NVSwitch box */
 
 typedef enum airgpu_status {
     AIRGPU_OK = 0,
@@ -119,6 +124,16 @@ int airgpu_submit(airgpu_ctx *ctx, const void *iq, size_t n_samples,
                   uint64_t base_offset, uint64_t *ticket);
 int airgpu_collect(airgpu_ctx *ctx, uint64_t ticket, airgpu_frame *out, size_t cap,
                    size_t *n_frames);
+/* The ring keeps room for the worst case on the device (a constant buffer yields a
+ * frame at every offset: max_buffer_samples - 240 records), so nothing is ever dropped
+ * there.  If `cap` is smaller than the buffer's frame count airgpu_collect returns
+ * AIRGPU_ERR_OVERFLOW with *n_frames = that count and KEEPS the ticket: collect it
+ * again with a larger array.  Only the records that exist cross PCIe (a small fixed
+ * head with the count, the rest on demand), not max_frames of them. */
+
+/* Samples of a capture of `len` samples that the reference's playback thread actually
+ * sends in chunks of `chunk` (src/adsb.rs:75-89: the last chunk is never sent). */
+size_t airgpu_playback_samples(size_t len, size_t chunk);
 
 /* ---- one-shot decode of a capture held in HOST memory -------------------- *
  * Chunks the capture through the pinned ring (H2D overlapped with compute,
@@ -144,6 +159,74 @@ int airgpu_decode_device(airgpu_ctx *ctx, const void *d_iq, size_t n_samples,
 int airgpu_sync_count(airgpu_ctx *ctx, uint64_t *n_frames);
 
 int airgpu_get_stats(airgpu_ctx *ctx, airgpu_stats *out);
+
+/* Pre-size the device workspace for captures of up to n_samples (cut into segments of
+ * segment_samples, 0 = one) and outputs of up to `cap` frames: later calls within these
+ * bounds neither allocate nor synchronise the device (a long-running streaming host
+ * calls this once after airgpu_create). */
+int airgpu_reserve(airgpu_ctx *ctx, size_t n_samples, size_t segment_samples, size_t cap);
+
+/* CUDA-event timing of the decode kernels (airgpu_stats.kernel_ms / decode_ms) on or off.
+ * Default on; off inside airgpu_graph_begin .. airgpu_graph_end automatically. */
+int airgpu_set_timing(airgpu_ctx *ctx, int enabled);
+
+/* ---- CUDA graphs: record a sequence of device-side calls once, replay it with one launch ---- *
+ * Between begin and end every airgpu_decode_device / airgpu_decode_device_peers /
+ * airgpu_decode_fields / airgpu_peer_barrier call on `stream` is captured instead of
+ * executed (cudaStreamBeginCapture); the workspace must already be large enough
+ * (airgpu_reserve or one eager call first), otherwise the call fails with
+ * AIRGPU_ERR_INVALID instead of allocating.  A launch replays the recorded work on the
+ * same buffers: a 20 000-sample buffer costs one launch instead of five. */
+typedef struct airgpu_graph airgpu_graph;
+int airgpu_graph_begin(airgpu_ctx *ctx, void *stream);
+int airgpu_graph_end(airgpu_ctx *ctx, void *stream, airgpu_graph **out);
+int airgpu_graph_launch(airgpu_graph *graph, void *stream);
+void airgpu_graph_destroy(airgpu_graph *graph);
+
+/* ---- multi-GPU: the frame exchange fused into the ordering kernels ---------------- *
+ * A long capture shards into contiguous candidate ranges (+240-sample halo), one per
+ * GPU; the only exchange is the per-GPU ordered frame lists.  Instead of
+ * decoding into a local array and copying it to the peers afterwards, the kernels that
+ * put the records in order store each record -- and the frame count -- straight to
+ * every destination: device-accessible addresses in this GPU's own memory, in peer
+ * GPUs' memory (cudaDeviceEnablePeerAccess / CUDA IPC / symmetric memory), or ONE
+ * NVSwitch multicast address (`multicast` = 1: multimem.st, the switch replicates).
+ * All destinations receive the same `cap`-record array layout. */
+typedef struct airgpu_peers {
+    uint32_t      struct_size;              /* sizeof(airgpu_peers)                         */
+    uint32_t      n_outs;                   /* 1 .. AIRGPU_MAX_PEERS                        */
+    uint32_t      multicast;                /* 1: outs[0] / counts[0] are multicast addresses */
+    uint32_t      reserved;
+    airgpu_frame *outs[AIRGPU_MAX_PEERS];
+    uint64_t     *counts[AIRGPU_MAX_PEERS]; /* may be NULL: no count written there         */
+} airgpu_peers;
+int airgpu_decode_device_peers(airgpu_ctx *ctx, const void *d_iq, size_t n_samples,
+                               size_t segment_samples, uint64_t base_offset,
+                               const airgpu_peers *dst, size_t cap, void *stream);
+/* One-kernel barrier across the ranks of an exchange: flags[q] is rank q's array of
+ * n_ranks epochs (zero-initialised) as mapped in this process; every rank calls it with
+ * the same, increasing `epoch`.  After it, the records every rank stored before its own
+ * call are visible here.  One rank per GPU. */
+int airgpu_peer_barrier(airgpu_ctx *ctx, uint64_t *const *flags, uint32_t n_ranks, uint32_t rank,
+                        uint64_t epoch, void *stream);
+
+/* ---- multi-GPU from ONE host thread (what the Rust decode thread can call) --------- *
+ * A group owns one context per listed device (a device may be listed more than once).
+ * airgpu_group_decode shards a capture held in HOST memory over them (contiguous
+ * candidate ranges + 240-sample halo), runs every shard's H2D copies and kernels
+ * concurrently, and returns the concatenated frame list: rank order == ascending
+ * offset == the reference's order, identical to airgpu_decode on one GPU. */
+typedef struct airgpu_group airgpu_group;
+int airgpu_group_create(const int *devices, uint32_t n_devices, uint32_t format, airgpu_group **out);
+int airgpu_group_decode(airgpu_group *grp, const void *iq, size_t n_samples, uint64_t base_offset,
+                        airgpu_frame *out, size_t cap, size_t *n_frames);
+/* per-shard counters of the last airgpu_group_decode (stats[k] for devices[k]) */
+int airgpu_group_stats(airgpu_group *grp, airgpu_stats *stats, uint32_t n_stats);
+void airgpu_group_destroy(airgpu_group *grp);
+/* Convenience: create a group, decode once, destroy it (SURVEY 8(b) "airgpu_decode_sharded"). */
+int airgpu_decode_sharded(const int *devices, uint32_t n_devices, uint32_t format, const void *iq,
+                          size_t n_samples, uint64_t base_offset, airgpu_frame *out, size_t cap,
+                          size_t *n_frames);
 
 /* ---- next row N1: frame field decode on the device ---------------------------- *
  * What AdsbPacket::new derives from the 14 bytes (src/adsb/packet.rs:25-49) and the

@@ -72,8 +72,8 @@ def _assert_reference_values(last, fields, frames):
     f = by_hex[ALT_FRAME]
     assert f["kind"] == 2 and f["altitude"] == 2600
     fa0, fa1 = by_hex[PAIR_A[0].lower()], by_hex[PAIR_A[1].lower()]
-    assert (fa0["cpr_latitude"], fa0["cpr_longitude"], fa0["cpr_odd"]) == (93000, 51372, 0)      # msgs.rs:303-321
-    assert (fa1["cpr_latitude"], fa1["cpr_longitude"], fa1["cpr_odd"]) == (74158, 50194, 1)
+    assert (fa0["cpr_latitude"], fa0["cpr_longitude"], fa0["cpr_odd"]) == (74158, 50194, 1)      # msgs.rs:303-321
+    assert (fa1["cpr_latitude"], fa1["cpr_longitude"], fa1["cpr_odd"]) == (93000, 51372, 0)
     assert fa0["altitude"] == 38000 and fa1["altitude"] == 38000
     fb0, fb1 = by_hex[PAIR_B[0]], by_hex[PAIR_B[1]]
     assert (fb0["cpr_latitude"], fb0["cpr_longitude"], fb0["altitude"]) == (15489, 111562, 1425)  # aircraft.rs:217-248
