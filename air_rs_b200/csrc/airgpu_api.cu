@@ -88,8 +88,12 @@ struct airgpu_ctx {
     size_t max_frames = 0;
     size_t ring_cap = 0;                       // records per ring slot on the device
     cudaStream_t compute = nullptr, copy = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr, ev_sync = nullptr, evk0 = nullptr, evk1 = nullptr;
-    bool ev_valid = false, evh_valid = false, evk_valid = false, sync_valid = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr, ev_sync = nullptr;
+    bool ev_valid = false, evh_valid = false, sync_valid = false;
+    // event pairs around the decode-kernel launches since the last airgpu_get_stats (a ring: the newest kKernelEvents)
+    static constexpr size_t kKernelEvents = 64;
+    cudaEvent_t kev0[kKernelEvents] = {}, kev1[kKernelEvents] = {};
+    size_t kev_n = 0;
     bool timing = true;                        // record the CUDA events behind airgpu_stats
     bool capturing = false;                    // between airgpu_graph_begin and airgpu_graph_end
 
@@ -235,11 +239,12 @@ int enqueue_piece(airgpu_ctx *c, const void *d_iq, size_t n, size_t seg, uint64_
     p.group_base = c->group_base();
     p.force_ordered = c->force_ordered;
     const bool timed = c->timing && !c->capturing;
-    if (timed) CU(cudaEventRecord(c->evk0, stream));
+    const size_t kslot = c->kev_n % airgpu_ctx::kKernelEvents;
+    if (timed) CU(cudaEventRecord(c->kev0[kslot], stream));
     CU(launch_decode(c->format, p, stream));
     if (timed) {
-        CU(cudaEventRecord(c->evk1, stream));
-        c->evk_valid = true;
+        CU(cudaEventRecord(c->kev1[kslot], stream));
+        c->kev_n++;
     }
     CU(launch_finalize(p, dst, d_total, stream));
     c->stats.n_tiles += g.n_tiles;
@@ -279,8 +284,12 @@ void destroy_ctx(airgpu_ctx *c)
     if (c->ws) cudaFree(c->ws);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->out_dev) cudaFree(c->out_dev);
-    for (cudaEvent_t e : {c->ev0, c->ev1, c->evh0, c->evh1, c->ev_sync, c->evk0, c->evk1})
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->evh0, c->evh1, c->ev_sync})
         if (e) cudaEventDestroy(e);
+    for (size_t k = 0; k < airgpu_ctx::kKernelEvents; ++k) {
+        if (c->kev0[k]) cudaEventDestroy(c->kev0[k]);
+        if (c->kev1[k]) cudaEventDestroy(c->kev1[k]);
+    }
     if (c->compute) cudaStreamDestroy(c->compute);
     if (c->copy) cudaStreamDestroy(c->copy);
     delete c;
@@ -467,8 +476,10 @@ int airgpu_create(const airgpu_config *cfg, airgpu_ctx **out)
     CUX(cudaEventCreate(&c->ev1));
     CUX(cudaEventCreate(&c->evh0));
     CUX(cudaEventCreate(&c->evh1));
-    CUX(cudaEventCreate(&c->evk0));
-    CUX(cudaEventCreate(&c->evk1));
+    for (size_t k = 0; k < airgpu_ctx::kKernelEvents; ++k) {
+        CUX(cudaEventCreate(&c->kev0[k]));
+        CUX(cudaEventCreate(&c->kev1[k]));
+    }
     CUX(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     CUX(cudaHostAlloc(&c->h_counters, (kNumCounters + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
     memset(c->h_counters, 0, (kNumCounters + 1) * sizeof(unsigned long long));
@@ -513,7 +524,10 @@ int airgpu_set_timing(airgpu_ctx *c, int enabled)
 {
     if (!c) return fail(AIRGPU_ERR_INVALID, "ctx is NULL");
     c->timing = enabled != 0;
-    if (!c->timing) c->ev_valid = c->evh_valid = c->evk_valid = false;
+    if (!c->timing) {
+        c->ev_valid = c->evh_valid = false;
+        c->kev_n = 0;
+    }
     return AIRGPU_OK;
 }
 
@@ -630,11 +644,20 @@ int airgpu_get_stats(airgpu_ctx *c, airgpu_stats *out)
         CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         c->stats.kernel_ms = ms;
     }
-    if (c->evk_valid) {
-        float ms = 0.f;
-        CU(cudaEventSynchronize(c->evk1));
-        CU(cudaEventElapsedTime(&ms, c->evk0, c->evk1));
-        c->stats.decode_ms = ms;
+    if (c->kev_n) {
+        // average over the decode-kernel launches since the previous call (the newest kKernelEvents of them)
+        const size_t have = std::min(c->kev_n, airgpu_ctx::kKernelEvents);
+        double sum = 0.0;
+        for (size_t k = 0; k < have; ++k) {
+            const size_t slot = (c->kev_n - 1 - k) % airgpu_ctx::kKernelEvents;
+            float ms = 0.f;
+            CU(cudaEventSynchronize(c->kev1[slot]));
+            CU(cudaEventElapsedTime(&ms, c->kev0[slot], c->kev1[slot]));
+            sum += ms;
+        }
+        c->stats.decode_ms = (float)(sum / (double)have);
+        c->stats.decode_launches = (float)have;
+        c->kev_n = 0;
     }
     if (c->evh_valid) {
         float ms = 0.f;

@@ -1011,18 +1011,32 @@ cudaError_t launch_finalize(const DecodeParams &p, const OutSet &dst, unsigned l
 // before (the records of the gather kernels earlier in the stream) is visible to a peer that acquires it -- and
 // then waits until rank q's epoch shows up in its own array (flags[rank][q]).  Every rank runs on its own GPU
 // (never two ranks of one exchange on one device: they would wait for each other's kernel).
+// epoch == 0: the kernel counts for itself in flags[rank][n_ranks] (local memory), so that the same launch can be
+// replayed from a CUDA graph.
 __global__ void peer_barrier_kernel(const PeerFlags f)
 {
+    __shared__ unsigned long long s_epoch;
     const unsigned q = threadIdx.x;
+    if (q == 0) {
+        unsigned long long e = f.epoch;
+        if (e == 0ull) {
+            unsigned long long *mine = f.flags[f.rank] + f.n_ranks;
+            e = *mine + 1ull;
+            *mine = e;
+        }
+        s_epoch = e;
+    }
+    __syncthreads();
     if (q >= f.n_ranks) return;
+    const unsigned long long epoch = s_epoch;
     __threadfence_system();
     unsigned long long *theirs = f.flags[q] + f.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(f.epoch) : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
     const unsigned long long *mine = f.flags[f.rank] + q;
     unsigned long long seen;
     do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-    } while (seen < f.epoch);
+    } while (seen < epoch);
 }
 
 cudaError_t launch_peer_barrier(const PeerFlags &f, cudaStream_t stream)

@@ -61,7 +61,7 @@ class Stats(C.Structure):
         ("kernel_ms", C.c_float),
         ("h2d_ms", C.c_float),
         ("decode_ms", C.c_float),
-        ("reserved", C.c_float),
+        ("decode_launches", C.c_float),
     ]
 
 

@@ -6,14 +6,19 @@ samples shards naturally: the candidates [0, N-240) are cut into `world`
 contiguous ranges and rank r decodes samples [a_r, b_r + 240) as one segment with
 base_offset = a_r.  Every candidate is owned by exactly one rank; concatenating
 the per-rank frame lists in rank order is the reference's emission order.  The
-only exchange is the all-gather of those lists.
+only exchange is that of the per-rank ordered lists.
 
-One process per GPU; `torch.distributed` supplies the plumbing (NCCL on GPUs,
-gloo in the CPU tests).
+One process per GPU; `torch.distributed` supplies the rendezvous (NCCL on GPUs,
+gloo in the CPU tests).  The exchange itself is done by the library's own ordering
+kernels (airgpu_decode_device_peers): they store every ordered record -- and the
+frame count -- straight into every rank's slab, through one NVSwitch multicast
+address when the box offers one, else through the peer-mapped addresses.  NCCL's
+all-gather is kept as the third back end (and is what gloo runs in the CPU tests).
 """
 from __future__ import annotations
 
 import os
+import sys
 from typing import List, Tuple
 
 HALO = 240          # samples a candidate reads beyond its own offset, plus one (16 + 112*2)
@@ -71,30 +76,48 @@ def concat_gathered(slab, counts):
     return torch.cat(parts, dim=0) if parts else slab.new_zeros((0, RECORD_BYTES))
 
 
+def sub_ranges(cands: int, pieces: int, weights=None) -> List[Tuple[int, int]]:
+    """Cut a shard's candidates [0, cands) into `pieces` contiguous sub-shards on ALIGN boundaries.  Later ones are
+    smaller: only the LAST exchange of a step has nothing left to overlap with."""
+    pieces = max(1, min(pieces, max(1, cands // ALIGN)))
+    w = list(weights)[:pieces] if weights else ([float(pieces - k + 1) for k in range(pieces)] if pieces > 1 else [1.0])
+    acc = [sum(w[:k]) / sum(w) for k in range(pieces)]
+    b = [min(cands, int(cands * a) // ALIGN * ALIGN) for a in acc] + [cands]
+    return [(b[k], b[k + 1]) for k in range(pieces)]
+
+
 class ShardedDecoder:
-    """Decode one rank's shard in `pieces` sub-shards and exchange the frame lists with every
-    other rank without ever stalling the GPU on the host.
+    """Decode one rank's shard in `pieces` sub-shards and exchange the ordered frame lists with every other rank,
+    without ever stalling the GPU on the host.
 
-    Each rank's buffer for a piece starts with a 24-byte header whose first 8 bytes are the
-    frame count (the library writes it there itself: `d_count` of airgpu_decode_device points
-    at it), followed by the ordered records.  Only `slab` rows travel: not the worst-case
-    capacity but what the traffic needs (a little above the largest count seen so far, the
-    same on every rank because every rank sees all counts); `finish()` checks after the fact
-    that no rank produced more and repeats the exchange with more rows if one did.
+    Slab layout (every rank holds the same): [parity 2][piece P][rank W][1 + cap rows of 24 bytes]; row 0 of a slot is
+    a header whose first 8 bytes are the frame count, rows 1.. are the records.  Rank r's ordering kernels write
+    slot [parity][k][r] of EVERY rank's slab.
 
-    Two exchange back ends:
-      "p2p"  (default on NVLink boxes) -- every rank owns a symmetric-memory slab set
-             (torch.distributed._symmetric_memory, rendezvous over the NCCL group); a rank
-             copies its rows straight into its slot of every peer's slabs with plain device
-             copies on a high-priority stream, i.e. over NVLink by the copy engines, so the
-             exchange takes no SMs away from the decode kernel of the next piece.  One
-             symmetric-memory barrier per step makes the peers' writes visible.
-      "nccl" -- one ncclAllGather per piece (used by the CPU/gloo tests and as the fallback).
+    Back ends (`exchange`):
+      "multicast" -- the slab set lives in symmetric memory (torch.distributed._symmetric_memory: a CUDA VMM
+                  allocation mapped into every rank, plus one NVSwitch multicast mapping).  The library's gather
+                  kernel stores each record once, to the multicast address; the switch replicates it to all ranks.
+                  Per-rank NVLink egress: 1x its list.
+      "peers"  -- same slab, the gather kernel stores each record to every rank's peer-mapped address ((W-1)x egress).
+      "nccl"   -- records stay local, one ncclAllGather per sub-shard on a side stream (the portable fallback, and what
+                  the CPU tests run over gloo).
+      "auto"   -- multicast if the box offers it, else peers, else nccl; the reason for a downgrade is kept in
+                  `exchange_note` and printed to stderr -- never silent.
+    multicast / peers: a step is `pieces` x (memset + decode + scan + gather) and ONE barrier kernel
+    (airgpu_peer_barrier: release/acquire flags in the slab), all on the caller's stream, recorded once per parity
+    into a CUDA graph and replayed with one launch per step (`use_graph`).
+
+    Hazards: slabs are double-buffered by step parity and every step ends in a barrier, so a rank can only overwrite
+    slot [parity] again two steps later, after every peer has passed the barrier of the step in between -- and
+    therefore has executed everything it queued on its stream before that step, including the reads of `finish()`.
+    Consumers of `finish(concat=False)` views must queue their reads (on the same stream) before calling `step()` twice.
+
     Result order: rank-major, piece-minor == ascending offset == the reference's order.
     """
 
     def __init__(self, decoder, n_local: int, first_sample: int, pieces: int = 2, cap_per_piece: int = 0,
-                 group=None, exchange: str = "auto"):
+                 group=None, exchange: str = "auto", use_graph: bool = True, bytes_per_sample: int = 2):
         import torch
         import torch.distributed as dist
 
@@ -103,15 +126,12 @@ class ShardedDecoder:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.dev = torch.device("cuda", decoder.device)
+        self.bps = bytes_per_sample
         cands = max(0, n_local - HALO)
-        pieces = max(1, min(pieces, max(1, cands // ALIGN)))
-        # later sub-shards are smaller: only the LAST exchange is exposed (nothing left to overlap it)
-        w = [float(pieces - k + 1) for k in range(pieces)] if pieces > 1 else [1.0]
+        weights = None
         if os.environ.get("AIRGPU_PIECE_WEIGHTS"):
-            w = [float(x) for x in os.environ["AIRGPU_PIECE_WEIGHTS"].split(",")][:pieces]
-        acc = [sum(w[:k]) / sum(w) for k in range(pieces)]
-        b = [min(cands, int(cands * a) // ALIGN * ALIGN) for a in acc] + [cands]
-        self.ranges = [(b[k], b[k + 1]) for k in range(pieces)]   # same number of exchanges on every rank
+            weights = [float(x) for x in os.environ["AIRGPU_PIECE_WEIGHTS"].split(",")]
+        self.ranges = sub_ranges(cands, pieces, weights)          # same number of exchanges on every rank
         self.first = first_sample
         cap = cap_per_piece or max(1 << 14, (max(e - s for s, e in self.ranges) + HALO) // 200)   # ~4x dense traffic
         if self.world > 1:   # every rank must use the same row count
@@ -119,120 +139,230 @@ class ShardedDecoder:
             dist.all_reduce(c, op=dist.ReduceOp.MAX, group=group)
             cap = int(c.item())
         self.cap = cap
-        self.slab = cap                      # rows exchanged per rank and piece; shrinks after the first step
         P, W = len(self.ranges), self.world
-        # row 0 = header (frame count in its first 8 bytes), rows 1.. = records
-        self.out = [torch.zeros((cap + 1, RECORD_BYTES), dtype=torch.uint8, device=self.dev) for _ in range(P)]
-        self.hdr_host = torch.zeros((P, W), dtype=torch.int64).pin_memory()
-        # high priority: the exchange must get going while the decode kernel still has CTAs queued
-        self.comm = torch.cuda.Stream(device=self.dev, priority=-1)
-        self.decoded = [torch.cuda.Event() for _ in range(P)]
-        self.gathered = [torch.cuda.Event() for _ in range(P)]
-        self._first_step = True
-        self.exchange = "nccl"
+        self.rows = cap + 1
+        self.slot_bytes = self.rows * RECORD_BYTES
+        self.parity_bytes = P * W * self.slot_bytes
+        self.flags_off = 2 * self.parity_bytes                    # [W + 1] u64: epochs seen from each rank, own counter
+        self.hdr_host = torch.zeros((2, P, W), dtype=torch.int64).pin_memory()
+        self.step_no = 0
+        self.use_graph = use_graph
+        self._graphs = [None, None]
+        self._graph_key = None
+        self._own_stream = None
+        self.exchange_note = ""
         self.symm = None
-        self.gath = None
-        if exchange in ("auto", "p2p") and self.world > 1:
-            try:
-                import torch.distributed._symmetric_memory as symm
-
-                rows = P * W * (cap + 1)
-                self._symm_t = symm.empty(rows * RECORD_BYTES, dtype=torch.uint8, device=self.dev)
-                g = group if group is not None else dist.group.WORLD
-                self.symm = symm.rendezvous(self._symm_t, g.group_name)
-                self.gath_full = self._symm_t.view(P, W, cap + 1, RECORD_BYTES)
-                self.peer_slots = [
-                    [self.symm.get_buffer(q, (P, W, cap + 1, RECORD_BYTES), torch.uint8)[k][self.rank]
-                     for k in range(P)] for q in range(W)]
-                self.exchange = "p2p"
-            except Exception:
-                if exchange == "p2p":
-                    raise
-                self.symm = None
-
-    def _alloc(self):
-        import torch
-
-        P, W = len(self.ranges), self.world
-        if self.exchange == "p2p":
-            self.gath = [self.gath_full[k] for k in range(P)]
+        self.exchange = self._pick_exchange(exchange)
+        total_bytes = self.flags_off + 8 * (W + 1)
+        if self.exchange in ("multicast", "peers"):
+            self.decode_reserved = False
         else:
-            self.gath = [torch.empty((W, self.slab + 1, RECORD_BYTES), dtype=torch.uint8, device=self.dev)
-                         for _ in range(P)]
+            # nccl: local records, all-gathered into `gath` on a high-priority side stream
+            self._slab_t = torch.zeros(total_bytes, dtype=torch.uint8, device=self.dev)
+            self.base_ptrs = [self._slab_t.data_ptr()] * W
+            self.comm = torch.cuda.Stream(device=self.dev, priority=-1)
+            self.out = [torch.zeros((self.rows, RECORD_BYTES), dtype=torch.uint8, device=self.dev) for _ in range(P)]
+            self.decoded = [torch.cuda.Event() for _ in range(P)]
+            self.gathered = [torch.cuda.Event() for _ in range(P)]
+            self.slab_rows = self.rows                            # rows exchanged per rank and piece; shrinks after the first step
+        self._slab = self._slab_t.view(torch.uint8)[: 2 * self.parity_bytes].view(2, P, W, self.rows, RECORD_BYTES)
 
-    def _exchange(self, k):
+    # ------------------------------------------------------------------ set-up
+    def _pick_exchange(self, want: str) -> str:
+        import torch
         import torch.distributed as dist
 
-        rows = self.slab + 1
-        if self.exchange == "p2p":
-            for q in range(self.world):      # my rows -> my slot in every rank's slab set (NVLink copy engines)
-                self.peer_slots[(self.rank + q) % self.world][k][:rows].copy_(self.out[k][:rows], non_blocking=True)
-        elif self.world > 1:
-            dist.all_gather_into_tensor(self.gath[k].view(-1), self.out[k][:rows].reshape(-1), group=self.group)
-        else:
-            self.gath[k][0].copy_(self.out[k][:rows])
-        self.gathered[k].record(self.comm)
+        if want not in ("auto", "multicast", "peers", "nccl"):
+            raise ValueError(f"unknown exchange back end {want!r}")
+        if want == "nccl" or self.world == 1 and want == "auto":
+            return "nccl"
+        total_bytes = self.flags_off + 8 * (self.world + 1)
+        try:
+            import torch.distributed._symmetric_memory as symm
 
-    def _publish_counts(self):
-        """After every piece of a step has been exchanged: barrier (p2p), then the counts of all ranks
-        go to pinned host memory for finish()."""
-        if self.exchange == "p2p":
-            self.symm.barrier(channel=0)
-        for k in range(len(self.ranges)):
-            self.hdr_host[k].copy_(self.gath[k][:, 0, :8].contiguous().view(-1).view(dtype=self.hdr_host.dtype),
-                                   non_blocking=True)
+            t = symm.empty(total_bytes, dtype=torch.uint8, device=self.dev)
+            t.zero_()
+            g = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm.rendezvous(t, g.group_name)
+            self._slab_t, self.symm = t, hdl
+            self.base_ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self.mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.group)                        # every rank's slab is zeroed before anyone writes to it
+        except Exception as e:                                    # no symmetric memory on this box / build
+            if want != "auto":
+                raise
+            self.exchange_note = f"symmetric memory unavailable ({type(e).__name__}: {e}); NCCL all-gather instead"
+            print(f"[airgpu sharding] {self.exchange_note}", file=sys.stderr)
+            return "nccl"
+        if want == "multicast" and not self.mc_ptr:
+            raise RuntimeError("no NVSwitch multicast mapping for the symmetric slab on this box")
+        if want in ("auto", "multicast") and self.mc_ptr:
+            return "multicast"
+        if want == "auto":
+            self.exchange_note = "no multicast mapping; plain stores to every peer"
+            print(f"[airgpu sharding] {self.exchange_note}", file=sys.stderr)
+        return "peers"
 
-    def step(self, iq, bytes_per_sample: int = 2):
-        """Queue one pass over this rank's shard (CUDA tensor of interleaved IQ).  Asynchronous."""
+    def _slot_off(self, parity: int, k: int, r: int) -> int:
+        return parity * self.parity_bytes + (k * self.world + r) * self.slot_bytes
+
+    # ------------------------------------------------------------------ one step
+    def _enqueue_fused(self, base_ptr: int, parity: int, stream: int) -> None:
+        """pieces x (decode + ordering kernels storing to every rank) + one barrier, on `stream`."""
+        for k, (s, e) in enumerate(self.ranges):
+            off = self._slot_off(parity, k, self.rank)
+            if self.exchange == "multicast":
+                outs, counts = [self.mc_ptr + off + RECORD_BYTES], [self.mc_ptr + off]
+            else:
+                # own slab first, then the peers starting with the next rank (spreads the NVLink traffic)
+                order = [(self.rank + q) % self.world for q in range(self.world)]
+                outs = [self.base_ptrs[q] + off + RECORD_BYTES for q in order]
+                counts = [self.base_ptrs[q] + off for q in order]
+            self.dec.decode_device_peers(base_ptr + s * self.bps, e - s + HALO, outs, counts, self.cap, 0, self.first + s,
+                                         stream, multicast=self.exchange == "multicast")
+        self.dec.peer_barrier([p + self.flags_off for p in self.base_ptrs], self.rank, 0, stream)
+
+    def step(self, iq, bytes_per_sample: int = None):
+        """Queue one pass over this rank's shard (CUDA tensor of interleaved IQ) on the current stream.  Asynchronous."""
         import torch
 
-        if self.gath is None:
-            self._alloc()
-        compute = torch.cuda.current_stream(self.dev)
+        if bytes_per_sample is not None:
+            self.bps = bytes_per_sample
+        cur = torch.cuda.current_stream(self.dev)
+        stream = cur
+        if cur.cuda_stream == 0:
+            # the legacy default stream: the library would fall back to its own (non-blocking) compute stream, which is
+            # not ordered against it -- run the step on a private stream bracketed by the default stream instead
+            if self._own_stream is None:
+                self._own_stream = torch.cuda.Stream(device=self.dev)
+            stream = self._own_stream
+            stream.wait_stream(cur)
+        parity = self.step_no & 1
+        if self.exchange == "nccl":
+            self._step_nccl(iq, parity, stream)
+        else:
+            if not self.decode_reserved:
+                # size the workspace once: nothing may allocate inside a graph capture
+                self.dec.reserve(max(e - s for s, e in self.ranges) + HALO, 0, self.cap)
+                self.decode_reserved = True
+            key = (iq.data_ptr(), stream.cuda_stream)
+            if self.use_graph and self._graph_key != key:
+                for g in self._graphs:
+                    if g is not None:
+                        g.close()
+                self._graphs, self._graph_key = [None, None], key
+            if self.use_graph and self._graphs[parity] is None and self.step_no >= 2:
+                # record this parity's sequence once (steps 0 and 1 run eagerly: they warm everything up)
+                self.dec.graph_begin(stream.cuda_stream)
+                try:
+                    self._enqueue_fused(iq.data_ptr(), parity, stream.cuda_stream)
+                finally:
+                    self._graphs[parity] = self.dec.graph_end(stream.cuda_stream)
+            if self.use_graph and self._graphs[parity] is not None:
+                self._graphs[parity].launch(stream.cuda_stream)
+            else:
+                self._enqueue_fused(iq.data_ptr(), parity, stream.cuda_stream)
+            with torch.cuda.stream(stream):
+                self.hdr_host[parity].copy_(self._slab[parity, :, :, 0, :8].contiguous().view(-1).view(torch.int64)
+                                            .view(len(self.ranges), self.world), non_blocking=True)
+        if stream is not cur:
+            cur.wait_stream(stream)
+        self.last_stream = stream
+        self.step_no += 1
+
+    def _step_nccl(self, iq, parity: int, compute) -> None:
+        import torch
+        import torch.distributed as dist
+
+        P = len(self.ranges)
         base_ptr = iq.data_ptr()
         for k, (s, e) in enumerate(self.ranges):
-            if not self._first_step:
+            if self.step_no > 0:
                 compute.wait_event(self.gathered[k])     # out[k] of the previous step has been sent
             o = self.out[k]
-            self.dec.decode_device(base_ptr + s * bytes_per_sample, e - s + HALO, o.data_ptr() + RECORD_BYTES,
+            self.dec.decode_device(base_ptr + s * self.bps, e - s + HALO, o.data_ptr() + RECORD_BYTES,
                                    self.cap, 0, self.first + s, o.data_ptr(), compute.cuda_stream)
             self.decoded[k].record(compute)
-        self._first_step = False
+        rows = self.slab_rows
         with torch.cuda.stream(self.comm):
-            for k in range(len(self.ranges)):
+            for k in range(P):
                 self.comm.wait_event(self.decoded[k])
-                self._exchange(k)
-            self._publish_counts()
+                dst = self._slab[parity, k, :, :rows]
+                if self.world > 1:
+                    tmp = torch.empty((self.world, rows, RECORD_BYTES), dtype=torch.uint8, device=self.dev)
+                    dist.all_gather_into_tensor(tmp.view(-1), self.out[k][:rows].reshape(-1), group=self.group)
+                    dst.copy_(tmp)
+                else:
+                    dst[0].copy_(self.out[k][:rows])
+                self.gathered[k].record(self.comm)
+            self.hdr_host[parity].copy_(self._slab[parity, :, :, 0, :8].contiguous().view(-1).view(torch.int64)
+                                        .view(P, self.world), non_blocking=True)
+
+    def wait(self) -> None:
+        """Make the current stream wait for the exchange of the last queued step (a timed region ends here)."""
+        import torch
+
+        if self.exchange == "nccl":
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm)
 
     def finish(self, concat: bool = True):
         """Wait for the last queued step; returns (frames [n, 24] in global order, n)."""
         import torch
 
-        self.comm.synchronize()
-        counts = self.hdr_host.clone()
+        if self.step_no == 0:
+            raise RuntimeError("finish() before any step()")
+        if self.exchange == "nccl":
+            self.comm.synchronize()
+        self.last_stream.synchronize()
+        parity = (self.step_no - 1) & 1
+        counts = self.hdr_host[parity].clone()
         m = int(counts.max())
         if m > self.cap:
             raise ValueError(f"a sub-shard produced {m} frames but the buffers hold {self.cap}")
-        if m > self.slab:
-            # optimistic row count was too small (traffic got denser): exchange again with room to spare
-            self.slab = min(self.cap, (int(m * 1.25) + 1023) // 1024 * 1024)
-            if self.exchange != "p2p":
-                self._alloc()
-            with torch.cuda.stream(self.comm):
-                for k in range(len(self.ranges)):
-                    self._exchange(k)
-                self._publish_counts()
-            self.comm.synchronize()
-            counts = self.hdr_host.clone()
-        elif self.slab == self.cap and m < self.cap:
-            self.slab = min(self.cap, (int(m * 1.15) + 1023) // 1024 * 1024)   # first step done: size for the traffic
-            if self.exchange != "p2p":
-                keep = self.gath
-                self.gath = [g[:, : self.slab + 1].contiguous() for g in keep]
+        if self.exchange == "nccl":
+            if m + 1 > self.slab_rows:
+                # optimistic row count was too small (traffic got denser): repeat the exchange with room to spare
+                self.slab_rows = min(self.rows, (int(m * 1.25) + 1024) // 1024 * 1024)
+                self.step_no -= 1
+                with torch.cuda.stream(self.last_stream):
+                    self._redo_nccl(parity)
+                self.step_no += 1
+                self.comm.synchronize()
+                counts = self.hdr_host[parity].clone()
+            elif self.slab_rows == self.rows and m + 1 < self.rows:
+                self.slab_rows = min(self.rows, (int(m * 1.15) + 1024) // 1024 * 1024)   # first step done: size for the traffic
         parts, total = [], 0
         for r in range(self.world):
             for k in range(len(self.ranges)):
                 c = int(counts[k, r])
-                parts.append(self.gath[k][r, 1 : 1 + c])
+                parts.append(self._slab[parity, k, r, 1: 1 + c])
                 total += c
         return (torch.cat(parts) if concat else parts), total
+
+    def _redo_nccl(self, parity: int) -> None:
+        import torch
+        import torch.distributed as dist
+
+        rows = self.slab_rows
+        with torch.cuda.stream(self.comm):
+            for k in range(len(self.ranges)):
+                dst = self._slab[parity, k, :, :rows]
+                if self.world > 1:
+                    tmp = torch.empty((self.world, rows, RECORD_BYTES), dtype=torch.uint8, device=self.dev)
+                    dist.all_gather_into_tensor(tmp.view(-1), self.out[k][:rows].reshape(-1), group=self.group)
+                    dst.copy_(tmp)
+                else:
+                    dst[0].copy_(self.out[k][:rows])
+            self.hdr_host[parity].copy_(self._slab[parity, :, :, 0, :8].contiguous().view(-1).view(torch.int64)
+                                        .view(len(self.ranges), self.world), non_blocking=True)
+
+    def launches_per_step(self) -> int:
+        """Kernels of this library launched per step on this rank (decode, scan, gather per sub-shard + the barrier)."""
+        return 3 * len(self.ranges) + (1 if self.exchange != "nccl" else 0)
+
+    def close(self) -> None:
+        for g in self._graphs:
+            if g is not None:
+                g.close()
+        self._graphs = [None, None]

@@ -16,10 +16,19 @@ on this configuration ("target: >= 60 % of HBM roofline per GPU on a 1 h
 synthetic capture"), and it fits one GPU, so it is the N = 1 workload too.
 
 A step = one pass of the whole hot path over the capture: decode kernel +
-ordering (scan, gather) into the reference-ordered frame list; for N > 1 the
+ordering (scan, gather) into the reference-ordered frame list.  For N > 1 the
 capture is cut into N contiguous candidate ranges (+240-sample halo), one per
-rank, and the per-rank lists are all-gathered over NCCL ("scaling": "strong").
+rank ("scaling": "strong"), and the per-rank lists are exchanged by the ordering
+kernels themselves: every record is stored once to an NVSwitch multicast address
+(or to every peer's mapped address; NCCL all-gather as the fallback) -- the line
+says which back end ran (`frame_exchange`).  The gathered list is compared byte
+for byte with rank 0's single-GPU decode of the whole capture inside the run.
 Inputs (17 GB) are far larger than L2 (126 MB), so no explicit flush is needed.
+
+Extra blocks of the N = 1 line: `cs16` (the reference's native sample format,
+4 B/sample, with its own roofline), `config4` (BASELINE configs[3]: 64 streams x
+256 KiB per batch, per-batch latency p50/p99, device-resident eager / graph and
+from host buffers), `cpu_baseline`.
 """
 from __future__ import annotations
 
@@ -44,6 +53,7 @@ SIGMA = 2.0
 HALO = 240
 CPU_SAMPLE = int(os.environ.get("AIRGPU_CPU_SAMPLES", 240_000_000))   # bounded CPU sample: first 100 s of the capture
 REF_SAMPLE = int(os.environ.get("AIRGPU_REF_SAMPLES", 240_000_000))
+CS16_SAMPLES = int(os.environ.get("AIRGPU_CS16_SAMPLES", 2_400_000_000))
 METRIC = "Msamples/s IQ->CRC-valid frames"
 UNIT = "Msamples/s"
 
@@ -51,12 +61,12 @@ UNIT = "Msamples/s"
 TRAFFIC = os.environ.get("AIRGPU_TRAFFIC", "dense")   # "sparse" = config 1's density (supplementary runs only)
 
 
-def traffic_table():
+def traffic_table(sigma=SIGMA):
     from air_rs_b200 import synth
 
     if TRAFFIC == "sparse":
-        return synth.make_traffic(SEED, PERIOD, df17_per_s=200.0, decoy_per_s=0.0, snr_db=(20.0, 20.0), sigma=SIGMA)
-    return synth.make_traffic(SEED, PERIOD, df17_per_s=3000.0, decoy_per_s=3000.0, snr_db=(8.0, 30.0), sigma=SIGMA)
+        return synth.make_traffic(SEED, PERIOD, df17_per_s=200.0, decoy_per_s=0.0, snr_db=(20.0, 20.0), sigma=sigma)
+    return synth.make_traffic(SEED, PERIOD, df17_per_s=3000.0, decoy_per_s=3000.0, snr_db=(8.0, 30.0), sigma=sigma)
 
 
 def workload_config(n_gpus: int, total: int) -> dict:
@@ -72,6 +82,21 @@ def workload_config(n_gpus: int, total: int) -> dict:
         "l2": "inputs (>= 2 GB per GPU) larger than the 126 MB L2; no flush needed",
         "generator_seed": SEED,
     }
+
+
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pin this process to the CPUs NVML names as closest to its GPU, BEFORE any pinned buffer is allocated, so
+    that page-locked host memory is first-touched on the GPU's own NUMA node (end-to-end ingest did
+    not scale from 2 to 4 GPUs)."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        nv.nvmlDeviceSetCpuAffinity(h)
+        return f"nvml ideal CPUs ({len(os.sched_getaffinity(0))} cores)"
+    except Exception as e:
+        return f"unchanged ({type(e).__name__})"
 
 
 class ClockSampler(threading.Thread):
@@ -122,18 +147,166 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def load_peak():
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (of fallback)"
+
+
+def cs16_block(dev, local, stream, peak, peak_src):
+    """The reference's native sample format (Vec<Complex<i16>>, src/adsb.rs:54-59): same traffic, 4 B/sample."""
+    import torch
+
+    from air_rs_b200 import synth
+    from air_rs_b200.decoder import AdsbDecoder
+    from air_rs_b200.native import FMT_CS16, FRAME_DTYPE
+
+    n = CS16_SAMPLES
+    gen = synth.DeviceSynth(traffic_table(sigma=300.0), device=local)
+    iq = gen.render(SEED, 0, n, FMT_CS16, 300.0, period=PERIOD)
+    dec = AdsbDecoder(fmt=FMT_CS16, device=local)
+    cap = max(1 << 16, n // 240)
+    out = torch.empty((cap, FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def run():
+        dec.decode_device(iq.data_ptr(), n, out.data_ptr(), cap, 0, 0, cnt.data_ptr(), stream.cuda_stream)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    dec.stats()                                         # drop the warm-up launches' events
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(10):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    kernel_ms = float(dec.stats()["decode_ms"])         # average over the ten timed launches
+    frames = int(cnt.item())
+    alg = 4.0 * n + 24.0 * frames
+    # the oracle on a slice of the same capture
+    from oracle import oracle_c
+
+    ns = 4_000_000
+    want, _ = oracle_c.decode_fast(iq[: 2 * ns].cpu().numpy(), threads=os.cpu_count() or 1)
+    got = AdsbDecoder.frames_from_tensor(out, frames)
+    got = got[got["offset"] < ns - HALO]
+    res = {
+        "value": round(n / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "samples": n, "bytes_per_sample": 4, "ms_per_step": round(ms, 4),
+        "frames_per_step": frames,
+        "workload": "same traffic mix, CS16 (reference-native: interleaved little-endian i16 I,Q), noise sigma 300",
+        "roofline": {"bound": "hbm", "achieved": round(alg / (kernel_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(alg / (kernel_ms * 1e-3) / 1e9 / peak, 4), "kernel": "decode_kernel<CS16>",
+                     "kernel_ms": round(kernel_ms, 4), "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+        "frames_equal_oracle_on_slice": bool(got.tobytes() == want.tobytes()), "slice_samples": ns,
+    }
+    dec.close()
+    gen.close()
+    del iq, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def config4_block(dev, local, stream):
+    """BASELINE configs[3]: 64 concurrent independent streams batched per 256 KiB buffer (131 072 samples u8 each,
+    INDEPENDENT segments: candidates [0, 131072-240) per stream, no halo -- exactly adsb.rs:98 per buffer).
+    Per-batch latency, device-resident (eager launches and one CUDA-graph launch) and from host buffers."""
+    import torch
+
+    from air_rs_b200 import synth
+    from air_rs_b200.decoder import AdsbDecoder
+    from air_rs_b200.native import FMT_U8, FRAME_DTYPE
+    from oracle import oracle_c
+
+    streams, per = 64, 131_072
+    n = streams * per
+    gen = synth.DeviceSynth(traffic_table(), device=local)
+    iq = gen.render(SEED + 4, 0, n, FMT_U8, SIGMA, period=PERIOD)
+    dec = AdsbDecoder(fmt=FMT_U8, device=local)
+    cap = 1 << 16
+    out = torch.empty((cap, FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    dec.reserve(n, per, cap)
+
+    def eager():
+        dec.decode_device(iq.data_ptr(), n, out.data_ptr(), cap, per, 0, cnt.data_ptr(), stream.cuda_stream)
+
+    def lat(fn, reps=300):
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            a.record(stream)
+            fn()
+            b.record(stream)
+            stream.synchronize()          # per-buffer latency: one batch in flight at a time
+        us = np.array([a.elapsed_time(b) * 1e3 for a, b in ev])
+        return {"p50_us": round(float(np.percentile(us, 50)), 1), "p99_us": round(float(np.percentile(us, 99)), 1)}
+
+    dec.set_timing(False)
+    res = {"workload": "config4: 64 streams x 256 KiB u8 per batch (8 388 608 samples), independent buffers",
+           "device_resident_eager": lat(eager)}
+    eager()
+    torch.cuda.synchronize()
+    frames = int(cnt.item())
+    dec.graph_begin(stream.cuda_stream)
+    eager()
+    g = dec.graph_end(stream.cuda_stream)
+    res["device_resident_graph"] = lat(lambda: g.launch(stream.cuda_stream))
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == frames
+    g.close()
+    dec.set_timing(True)
+    # parity of the batch: every stream is an independent segment
+    host = iq.cpu().numpy()
+    want, _ = oracle_c.decode_fast(host, per, 0, threads=os.cpu_count() or 1)
+    got = AdsbDecoder.frames_from_tensor(out, frames)
+    res["frames_per_batch"] = frames
+    res["frames_equal_oracle"] = bool(got.tobytes() == want.tobytes())
+    # from host buffers through airgpu_decode (pinned), wall clock around the synchronous call
+    import ctypes as C
+
+    from air_rs_b200 import native
+
+    h_iq = torch.empty(2 * n, dtype=torch.uint8, pin_memory=True)
+    h_iq.copy_(iq)
+    torch.cuda.synchronize()
+    h_out = np.zeros(cap, dtype=FRAME_DTYPE)
+    n_out = C.c_size_t(0)
+    wall = []
+    for k in range(120):
+        t0 = time.perf_counter()
+        native.check(native.lib().airgpu_decode(dec._h, h_iq.data_ptr(), n, per, 0, h_out.ctypes.data, cap, C.byref(n_out)))
+        if k >= 20:
+            wall.append((time.perf_counter() - t0) * 1e6)
+    res["host_buffers"] = {"p50_us": round(float(np.percentile(wall, 50)), 1), "p99_us": round(float(np.percentile(wall, 99)), 1),
+                           "h2d_bytes": 2 * n, "d2h_bytes": int(24 * n_out.value + 40),
+                           "frames_equal_oracle": bool(h_out[: n_out.value].tobytes() == want.tobytes())}
+    res["per_stream_buffer_us_at_2.4MSps"] = round(per / 2.4, 1)      # a 256 KiB buffer holds 54.6 ms of one stream
+    dec.close()
+    gen.close()
+    return res
+
+
 def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    affinity = bind_to_gpu_numa_node(local)
+
     import torch
 
     from air_rs_b200 import synth
     from air_rs_b200.decoder import AdsbDecoder
     from air_rs_b200.native import FMT_U8, FRAME_DTYPE
 
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -164,14 +337,15 @@ def run_ours(args):
     assert stream != 0
     state = {"frames": 0, "gathered": None}
     pieces = 1 if world == 1 else int(os.environ.get("AIRGPU_PIECES", 2))
-    sharded = (sharding.ShardedDecoder(dec, n_local, a, pieces=pieces, exchange=os.environ.get("AIRGPU_EXCHANGE", "auto"))
+    sharded = (sharding.ShardedDecoder(dec, n_local, a, pieces=pieces, exchange=os.environ.get("AIRGPU_EXCHANGE", "auto"),
+                                       use_graph=os.environ.get("AIRGPU_GRAPH", "1") != "0")
                if world > 1 else None)
 
     def decode_resident():
         dec.decode_device(iq.data_ptr(), n_local, out.data_ptr(), cap, 0, a, d_count.data_ptr(), stream)
 
     def gather():
-        """NCCL all-gather of the per-rank ordered lists (rank order == offset order)."""
+        """NCCL all-gather of per-rank ordered lists (the end-to-end leg only: its lists start in host memory)."""
         slab, counts = sharding.allgather_frames(out, d_count)
         state["gathered"] = (slab, counts)
         state["frames"] = int(counts.sum())
@@ -180,8 +354,8 @@ def run_ours(args):
         if world == 1:
             decode_resident()
         else:
-            # sub-shards decoded back to back; each one's all-gather overlaps the next decode;
-            # no host synchronisation inside a step (sharding.ShardedDecoder)
+            # sub-shards decoded back to back, every record stored straight into every rank's slab by the ordering
+            # kernels, one barrier kernel per step; no host synchronisation inside a step (sharding.ShardedDecoder)
             sharded.step(iq)
 
     def barrier():
@@ -193,7 +367,7 @@ def run_ours(args):
         for _ in range(warmup):
             fn()
             if sharded is not None and fn is step:
-                state["gathered"], state["frames"] = sharded.finish()   # also sizes the exchange slabs
+                state["gathered"], state["frames"] = sharded.finish()
         barrier()
         if sampler:
             sampler.active.set()
@@ -202,7 +376,7 @@ def run_ours(args):
         for _ in range(steps):
             fn()
         if sharded is not None and fn is step:
-            tstream.wait_stream(sharded.comm)     # the step ends when the last all-gather has landed
+            sharded.wait()                        # the step ends when the last exchange has landed
         e1.record()
         torch.cuda.synchronize()
         if sampler:
@@ -217,10 +391,12 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_total = timed(step, args.steps, args.warmup, sampler)
+    dec.stats()                                 # forget the decode-kernel events of everything before the timed region
+    ms_total = timed(step, args.steps, max(args.warmup, 4 if world > 1 else 3), sampler)   # N > 1: both graph parities recorded in warm-up
+    timed_stats = dec.stats()                   # N = 1: the decode kernel's own events INSIDE the timed region
     sampler.stop()
     ms_step = ms_total / args.steps
-    exchange_ok = None
+    exchange_ok = truth_ok = None
     if world > 1:
         decode_resident()                       # whole local shard once more, for the per-rank frame count
         torch.cuda.synchronize()
@@ -235,25 +411,47 @@ def run_ours(args):
                            torch.tensor(g.shape[0], device=dev)])
         offs = g[:, 16:24].contiguous().view(torch.int64).view(-1)
         exchange_ok = bool(torch.equal(chk, got)) and bool((offs[1:] > offs[:-1]).all()) if g.shape[0] > 1 else bool(torch.equal(chk, got))
-    n_frames_local = int(d_count.item())
+        # the truth: rank 0 decodes the WHOLE capture on its one GPU; every rank compares its gathered list byte for byte
+        if not args.no_truth:
+            n_all = int(g.shape[0])
+            ref = torch.zeros((max(n_all, 1), FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+            ref_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            if rank == 0:
+                whole = gen.render(SEED, 0, total, FMT_U8, SIGMA, period=PERIOD)
+                cap_all = max(n_all + 1024, 1 << 16)
+                with AdsbDecoder(fmt=FMT_U8, device=local) as dec1:       # its own context: its own workspace
+                    wout, wn = dec1.decode_tensor(whole, cap=cap_all)
+                ref_n.fill_(wn)
+                if wn == n_all:
+                    ref.copy_(wout[:n_all])
+                del whole, wout
+            dist.broadcast(ref_n, 0)
+            dist.broadcast(ref, 0)
+            same = torch.tensor([1 if (int(ref_n.item()) == n_all and bool(torch.equal(ref, g))) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            truth_ok = bool(int(same.item()))
+            del ref
+    n_frames_local = int(d_count.item()) if world > 1 else None
     if world == 1:
+        torch.cuda.synchronize()
+        n_frames_local = int(d_count.item())
         state["frames"] = n_frames_local
     if n_frames_local > cap:
         raise SystemExit(f"frame capacity {cap} too small for {n_frames_local} frames")
     value = total / (ms_step * 1e-3) / 1e6
 
-    # dominant kernel alone (CUDA events around the decode kernel on its launch stream)
-    k_ms = []
-    for _ in range(max(3, min(args.steps, 10))):
-        decode_resident()
-        k_ms.append(dec.stats()["decode_ms"])
-    kernel_ms = float(np.mean(k_ms))
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dominant kernel alone: CUDA events around decode_kernel on its launch stream.  N = 1: the launches of the timed
+    # region itself (the library keeps an event pair per launch; warm-up launches were dropped above).  N > 1: the
+    # timed steps are graph replays (no events inside), so the rank's whole shard is decoded a few more times.
+    if world == 1 and timed_stats["decode_launches"] >= 1:
+        kernel_ms, kernel_launches = float(timed_stats["decode_ms"]), int(timed_stats["decode_launches"])
+    else:
+        dec.stats()
+        for _ in range(max(3, min(args.steps, 10))):
+            decode_resident()
+        st = dec.stats()
+        kernel_ms, kernel_launches = float(st["decode_ms"]), int(st["decode_launches"])
+    peak, peak_src = load_peak()
     alg_bytes = 2.0 * n_local + 24.0 * n_frames_local
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None      # dram__bytes_read + write of one launch, from the committed ncu capture of this workload
@@ -266,8 +464,11 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic,
-        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        "peak_source": peak_src,
         "kernel": "decode_kernel<U8>", "kernel_ms": round(kernel_ms, 4),
+        "kernel_launches_averaged": kernel_launches,
+        "kernel_timing": "CUDA events around each decode_kernel launch of the timed region" if world == 1 else
+                         "CUDA events around decode_kernel launches over the rank's whole shard, after the timed region",
         "algorithmic_bytes_per_launch": alg_bytes,
         "nominal_hbm_gbs": 8000,
     }
@@ -281,7 +482,7 @@ def run_ours(args):
         h_iq.copy_(iq)
         torch.cuda.synchronize()
         h_out = np.zeros(cap, dtype=FRAME_DTYPE)
-        got = {"n": 0}
+        got = {"n": 0, "h2d_ms": []}
 
         def e2e_step():
             import ctypes as C
@@ -292,6 +493,7 @@ def run_ours(args):
             native.check(native.lib().airgpu_decode(dec._h, h_iq.data_ptr(), n_local, 0, a, h_out.ctypes.data, cap,
                                                     C.byref(n_out)))
             got["n"] = n_out.value
+            got["h2d_ms"].append(dec.stats()["h2d_ms"])
             if world > 1:
                 d_count.fill_(n_out.value)
                 out[: n_out.value].copy_(torch.from_numpy(h_out[: n_out.value].view(np.uint8).reshape(-1, 24)))
@@ -299,16 +501,22 @@ def run_ours(args):
 
         k2 = max(1, min(args.steps, 5))
         barrier()
-        t0 = time.perf_counter()
         e2e_ms = timed(e2e_step, k2, 1)
-        wall = time.perf_counter() - t0
         # airgpu_decode is synchronous (it returns the frames), so CUDA events bracket host-side work too
         e2e_ms_step = e2e_ms / k2
+        h2d_ms = float(np.median(got["h2d_ms"][1:] or got["h2d_ms"]))
+        per_rank = torch.tensor([h2d_ms, 2.0 * n_local / (h2d_ms * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(per_rank) for _ in range(world)] if world > 1 else [per_rank]
+        if world > 1:
+            dist.all_gather(allr, per_rank)
         e2e = {
             "value": round(total / (e2e_ms_step * 1e-3) / 1e6, 1), "unit": UNIT,
             "h2d_bytes_per_step": int(2 * n_local), "d2h_bytes_per_step": int(24 * got["n"] + 8),
             "ms_per_step": round(e2e_ms_step, 3), "steps": k2,
             "api": "airgpu_decode (C ABI), pinned host IQ -> host frame records",
+            "h2d_ms_per_rank": [round(float(x[0]), 2) for x in allr],
+            "h2d_gbs_per_rank": [round(float(x[1]), 1) for x in allr],
+            "host_cpu_affinity": affinity,
         }
         del h_iq
     except Exception as e:  # e.g. not enough pinned host memory for the shard
@@ -347,22 +555,46 @@ def run_ours(args):
             "frames_on_sample": int(len(lit)),
         }
 
+    # ---- the other formats / configurations BASELINE names (N = 1 line only)
+    cs16 = config4 = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del iq
+        torch.cuda.empty_cache()
+        try:
+            cs16 = cs16_block(dev, local, tstream, peak, peak_src)
+        except Exception as e:
+            cs16 = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            config4 = config4_block(dev, local, tstream)
+        except Exception as e:
+            config4 = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
+        launches = 3 if world == 1 else sharded.launches_per_step()
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(world, total),
             "frames_per_step": state["frames"],
-            "gpu_launches": 3 * args.steps * pieces,
+            "gpu_launches": launches * args.steps,
             "pieces_per_rank": pieces,
             "frame_exchange": (sharded.exchange if sharded is not None else None),
+            "frame_exchange_detail": (None if sharded is None else {
+                "multicast": "ordering kernels store each record once to an NVSwitch multicast address (multimem.st)",
+                "peers": "ordering kernels store each record to every rank's peer-mapped slab",
+                "nccl": "ncclAllGather per sub-shard on a side stream"}[sharded.exchange]),
+            "frame_exchange_note": (sharded.exchange_note if sharded is not None else None),
+            "cuda_graph": (bool(sharded.use_graph and sharded.exchange != "nccl") if sharded is not None else False),
             "gathered_list_checks_out": exchange_ok,
-            "kernels_per_step": ["decode_kernel<U8>", "group_scan_kernel", "gather_kernel"],
+            "gathered_equals_single_gpu_decode_on_rank0": truth_ok,
+            "kernels_per_step": ["decode_kernel<U8>", "group_scan_kernel", "gather_kernel"] + (["peer_barrier_kernel"] if world > 1 and sharded.exchange != "nccl" else []),
             "clocks": sampler.summary(),
             "roofline": roofline,
             "e2e": e2e,
             "cpu_baseline": cpu,
+            "cs16": cs16,
+            "config4": config4,
             "hbm_gbs_whole_step": round(alg_bytes / (ms_step * 1e-3) / 1e9, 1) if world == 1 else None,
         }
         print(json.dumps(line))
@@ -370,34 +602,33 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _render_block(job):
+    from air_rs_b200 import synth
+
+    table, j, n = job
+    return synth.render(table, SEED, j, n, synth.FMT_U8, SIGMA, period=PERIOD)
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path.  The reference is Rust and
     cannot be built here (no rustc/cargo, no network), so this arm runs the LITERAL C
     restatement (oracle/adsb_oracle.c) chunk-parallel on every host core, on a bounded
-    sample of the same capture per step."""
+    sample of the same capture per step.  Nothing of the GPU library is loaded: the
+    input is rendered on the host by the numpy twin of the generator."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    from air_rs_b200 import synth
+    from concurrent.futures import ProcessPoolExecutor
+
     from oracle import oracle_c
 
     ncores = os.cpu_count() or 1
     ns = REF_SAMPLE
     table = traffic_table()
-    host = None
-    try:
-        import torch
-
-        if torch.cuda.is_available():
-            gen = synth.DeviceSynth(table, device=0)
-            host = gen.render(SEED, 0, ns, synth.FMT_U8, SIGMA, period=PERIOD).cpu().numpy()
-            gen.close()
-    except Exception:
-        host = None
-    if host is None:
-        blocks = [synth.render(table, SEED, j, min(4_000_000, ns - j), synth.FMT_U8, SIGMA, period=PERIOD)
-                  for j in range(0, ns, 4_000_000)]
-        host = np.concatenate(blocks)
+    block = 4_000_000
+    jobs = [(table, j, min(block, ns - j)) for j in range(0, ns, block)]
+    with ProcessPoolExecutor(max_workers=min(ncores, len(jobs))) as ex:
+        host = np.concatenate(list(ex.map(_render_block, jobs)))
     frames = 0
     for _ in range(args.warmup):
         oracle_c.decode_literal_mt(host, threads=ncores)
@@ -428,6 +659,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (kernel A/B runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cs16 and config4 blocks (kernel A/B runs)")
+    ap.add_argument("--no-truth", action="store_true", help="N > 1: skip the comparison with rank 0's single-GPU decode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -99,8 +99,9 @@ typedef struct airgpu_stats {
     uint64_t n_tiles;
     float    kernel_ms;      /* device time of the decode kernels (CUDA events), 0 if not measured */
     float    h2d_ms;         /* host->device copy time of the last host-buffer decode   */
-    float    decode_ms;      /* device time of the fused decode kernel alone (last piece) */
-    float    reserved;
+    float    decode_ms;      /* device time of the fused decode kernel alone: average over its launches since the
+                                previous airgpu_get_stats (the newest 64 of them), CUDA events on the launch stream */
+    float    decode_launches; /* how many launches that average covers                */
 } airgpu_stats;
 
 const char *airgpu_version(void);
@@ -205,8 +206,11 @@ int airgpu_decode_device_peers(airgpu_ctx *ctx, const void *d_iq, size_t n_sampl
                                const airgpu_peers *dst, size_t cap, void *stream);
 /* One-kernel barrier across the ranks of an exchange: flags[q] is rank q's array of
  * n_ranks epochs (zero-initialised) as mapped in this process; every rank calls it with
- * the same, increasing `epoch`.  After it, the records every rank stored before its own
- * call are visible here.  One rank per GPU. */
+ * the same, increasing `epoch` (>= 1).  After it, the records every rank stored before its
+ * own call are visible here.  epoch = 0: the kernel keeps the count itself in
+ * flags[rank][n_ranks] (the arrays then hold n_ranks + 1 words), so that one recorded
+ * launch can be replayed from a CUDA graph.  One rank per GPU: two ranks of one
+ * exchange on the same device would wait for each other's kernel. */
 int airgpu_peer_barrier(airgpu_ctx *ctx, uint64_t *const *flags, uint32_t n_ranks, uint32_t rank,
                         uint64_t epoch, void *stream);
 

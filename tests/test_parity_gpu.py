@@ -372,7 +372,9 @@ def test_cpp_host_harness_playback(tmp_path):
 
 
 def test_pipelined_sub_shards_equal_single_pass(dec_u8):
-    """sharding.ShardedDecoder (world 1): four sub-shards decoded back to back == one pass."""
+    """sharding.ShardedDecoder (world 1): four sub-shards decoded back to back == one pass, on a side stream and on the
+    legacy default stream (the library would otherwise decode on its own, unordered stream there), with the
+    all-gather back end's optimistic row count forced too small."""
     import torch
 
     from air_rs_b200 import sharding
@@ -385,20 +387,55 @@ def test_pipelined_sub_shards_equal_single_pass(dec_u8):
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         sd = sharding.ShardedDecoder(dec_u8, n, 5_000, pieces=4)
+        assert sd.exchange == "nccl"             # one rank: nothing to exchange with
         sd.step(t)
         frames, total = sd.finish()          # first step: full-capacity slabs, then sized to the traffic
         sd.step(t)
         sd.step(t)
         frames2, total2 = sd.finish()        # steady state: optimistic slabs, no host sync between steps
         assert total2 == total and torch.equal(frames, frames2)
-        sd.slab = 16                         # force the "slab too small" path
-        sd._alloc()
+        sd.slab_rows = 16                    # force the "slab too small" path
         sd.step(t)
         frames3, total3 = sd.finish()
         assert total3 == total and torch.equal(frames, frames3)
     got = frames.cpu().numpy().view(FRAME_DTYPE).reshape(-1)
     assert total == len(whole) and frames_equal(got, whole), describe_diff(got, whole)
+    # the legacy default stream
+    t2 = t.clone()
+    sd2 = sharding.ShardedDecoder(dec_u8, n, 5_000, pieces=2)
+    t2.zero_()
+    t2.copy_(t)                              # produced on the default stream right before the step
+    sd2.step(t2)
+    frames4, total4 = sd2.finish()
+    assert total4 == total and torch.equal(frames4, frames)
     dev.close()
+
+
+def test_multi_rank_exchange_equals_single_gpu_decode():
+    """under torchrun with N = 2 and N = all visible GPUs (<= 8), the list every rank ends up with --
+    for the multicast, peer-store and NCCL back ends, eager and graph-replayed -- is byte for byte the single-GPU
+    decode of the same capture.  One rank per GPU (two ranks of one exchange must never share a device), so the test
+    needs at least two GPUs; on a one-GPU box it says so."""
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    from air_rs_b200 import native
+
+    ndev = native.lib().airgpu_device_count()
+    if ndev < 2:
+        pytest.skip("the multi-rank exchange needs >= 2 GPUs (bench.py --gpus N repeats this check against rank 0's "
+                    "single-GPU decode inside the driver's scaling run)")
+    root = Path(__file__).resolve().parents[1]
+    for world in sorted({2, min(ndev, 8)}):
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), str(root / "tests" / "multi_rank_worker.py")],
+                           cwd=root, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        assert r.returncode == 0 and f"ALL OK world={world}" in r.stdout, r.stdout[-4000:] + r.stderr[-4000:]
 
 
 def test_unaligned_device_pointer_and_odd_sizes(dec_u8, dec_cs16):
