@@ -711,6 +711,13 @@ int airgpu_graph_end(airgpu_ctx *c, void *stream, airgpu_graph **out)
     return AIRGPU_OK;
 }
 
+int airgpu_set_capturing(airgpu_ctx *c, int capturing)
+{
+    if (!c) return fail(AIRGPU_ERR_INVALID, "ctx is NULL");
+    c->capturing = capturing != 0;
+    return AIRGPU_OK;
+}
+
 int airgpu_graph_launch(airgpu_graph *g, void *stream)
 {
     if (!g || !stream) return fail(AIRGPU_ERR_INVALID, "NULL argument");

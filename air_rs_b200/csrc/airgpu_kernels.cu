@@ -799,92 +799,124 @@ group_scan_kernel(const unsigned long long *group_sum, unsigned n_groups, unsign
 // kMode 0: one destination (plain decode); 1: dst.n destinations, plain stores to local / peer-mapped memory (the
 // frame exchange over NVLink, fused: no copy engine, no second kernel); 2: one multimem.st per word to an NVSwitch
 // multicast address -- the switch replicates it to every rank, so a rank's NVLink egress is 1x its list, not (n-1)x.
+// Copy `n_words` staged u64 words to word index `w0` of every destination with the widest stores the alignment
+// allows: a lone 8-byte word in front if needed, then 16-byte stores from consecutive threads (full 128-byte lines:
+// what NVLink wants -- 8-byte stores at a 24-byte stride reached a fraction of the link rate), then a lone word.
+//   kMode 0: one destination (plain decode); 1: dst.n destinations, plain stores to local / peer-mapped memory (the
+//   frame exchange over NVLink, fused: no copy engine, no second kernel); 2: one multimem.st per 16 bytes to an
+//   NVSwitch multicast address -- the switch replicates it to every rank, so a rank's NVLink egress is 1x its list.
 template <int kMode>
-__device__ __forceinline__ void store_record(const OutSet &o, unsigned long long dst, const uint4 q, uint32_t meta,
-                                             unsigned long long tile_off0)
+__device__ __forceinline__ void copy_out(const OutSet &o, unsigned long long w0, const unsigned long long *s_words, unsigned n_words)
 {
-    const unsigned long long w0 = (unsigned long long)__byte_perm(q.x, 0, 0x0123) |
-                                  ((unsigned long long)__byte_perm(q.y, 0, 0x0123) << 32);
-    const uint32_t hi = __byte_perm(q.w, meta >> 16, 0x7423);
-    const unsigned long long w1 = (unsigned long long)__byte_perm(q.z, 0, 0x0123) | ((unsigned long long)hi << 32);
-    const unsigned long long w2 = tile_off0 + (meta & 0xFFFFu);
-    if (kMode == 2) {
-        unsigned long long *out = o.out[0] + dst * 3;
-        multimem_st_u64(out, w0);
-        multimem_st_u64(out + 1, w1);
-        multimem_st_u64(out + 2, w2);
-    } else {
+    const unsigned ndst = kMode == 1 ? o.n : 1u;
 #pragma unroll 1
-        for (unsigned j = 0; j < (kMode == 0 ? 1u : o.n); ++j) {
-            unsigned long long *out = o.out[j] + dst * 3;
-            out[0] = w0;
-            out[1] = w1;
-            out[2] = w2;
+    for (unsigned j = 0; j < ndst; ++j) {
+        unsigned long long *dst = o.out[j] + w0;
+        const unsigned head = (unsigned)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1u) & (n_words ? 1u : 0u);   // words before 16-byte alignment
+        const unsigned pairs = (n_words - head) >> 1;
+        const unsigned tail = n_words - head - 2 * pairs;
+        if (threadIdx.x == 0 && head) {
+            if (kMode == 2) multimem_st_u64(dst, s_words[0]);
+            else dst[0] = s_words[0];
+        }
+        if (threadIdx.x == 1 && tail) {
+            if (kMode == 2) multimem_st_u64(dst + n_words - 1, s_words[n_words - 1]);
+            else dst[n_words - 1] = s_words[n_words - 1];
+        }
+        for (unsigned k = threadIdx.x; k < pairs; k += blockDim.x) {
+            const unsigned long long a = s_words[head + 2 * k], b = s_words[head + 2 * k + 1];
+            unsigned long long *q = dst + head + 2 * k;
+            if (kMode == 2) {
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "r"((uint32_t)a),
+                             "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)) : "memory");
+            } else {
+                *reinterpret_cast<uint4 *>(q) = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+            }
         }
     }
 }
+
+constexpr unsigned kGatherChunk = 1536;      // records staged in shared memory at a time (36 KB)
 
 template <int kMode>
 __global__ void __launch_bounds__(kGroupTiles)
 gather_kernel(const DecodeParams p, const unsigned long long *group_base, const OutSet out)
 {
-    // One CTA per group of kGroupTiles tiles: scan the counts in shared memory, then one
-    // THREAD per record of the group (binary search for its tile) so that all record copies of
-    // the group are independent loads in flight at once.  The fast path of decode_kernel fills a
-    // tile's slots in no particular order: a record's place among the (at most kSlotsPerTile)
-    // records of its tile is the number of them with a smaller offset.
+    // One CTA per group of kGroupTiles tiles: scan the counts in shared memory, then one THREAD per record of the
+    // group (binary search for its tile) so that all record loads of the group are in flight at once.  The fast
+    // path of decode_kernel fills a tile's slots in no particular order: a record's place among the (at most
+    // kSlotsPerTile) records of its tile is the number of them with a smaller offset.  The finished records of the
+    // group are staged in shared memory in output order -- they form ONE contiguous byte range of the output -- and
+    // leave with wide coalesced stores.
     __shared__ unsigned long long s_warp[33];
     __shared__ unsigned int s_excl[kGroupTiles + 1];
     __shared__ unsigned int s_ovf[kGroupTiles];
+    __shared__ __align__(16) unsigned long long s_words[3 * kGatherChunk];
     const unsigned t0 = blockIdx.x * kGroupTiles;
     const unsigned t = t0 + threadIdx.x;
     const uint2 e = t < p.n_tiles ? p.tile_tab[t] : make_uint2(0u, 0u);
-    unsigned long long total;
-    const unsigned long long excl = block_exclusive_scan(e.y, s_warp, &total);
-    if (total == 0) return;
+    unsigned long long total64;
+    const unsigned long long excl = block_exclusive_scan(e.y, s_warp, &total64);
+    if (total64 == 0) return;
     s_excl[threadIdx.x] = (unsigned)excl;
     s_ovf[threadIdx.x] = e.x;
-    if (threadIdx.x == 0) s_excl[kGroupTiles] = (unsigned)total;
+    if (threadIdx.x == 0) s_excl[kGroupTiles] = (unsigned)total64;
     __syncthreads();
     const unsigned long long gbase = group_base[blockIdx.x];
+    if (gbase >= p.cap) return;
+    // records beyond the output's capacity are counted (the caller learns the total) but not written
+    const unsigned total = (unsigned)min(total64, p.cap - gbase);
     const uint4 *scratch = reinterpret_cast<const uint4 *>(p.scratch);
-    for (unsigned r = threadIdx.x; r < (unsigned)total; r += kGroupTiles) {
-        // largest k with s_excl[k] <= r (tiles with zero frames share their successor's value)
-        unsigned lo = 0, hi = kGroupTiles;
-        while (hi - lo > 1) {
-            const unsigned mid = (lo + hi) >> 1;
-            if (s_excl[mid] <= r) lo = mid;
-            else hi = mid;
+    for (unsigned c0 = 0; c0 < total; c0 += kGatherChunk) {
+        const unsigned c1 = min(total, c0 + kGatherChunk);
+        // a record's place differs from its slot by less than kSlotsPerTile (unordered tiles hold at most that many)
+        const unsigned r0 = c0 >= (unsigned)kSlotsPerTile ? c0 - kSlotsPerTile : 0u;
+        const unsigned r1 = (unsigned)min(total64, (unsigned long long)c1 + kSlotsPerTile);
+        for (unsigned r = r0 + threadIdx.x; r < r1; r += kGroupTiles) {
+            // largest k with s_excl[k] <= r (tiles with zero frames share their successor's value)
+            unsigned lo = 0, hi = kGroupTiles;
+            while (hi - lo > 1) {
+                const unsigned mid = (lo + hi) >> 1;
+                if (s_excl[mid] <= r) lo = mid;
+                else hi = mid;
+            }
+            const unsigned idx = r - s_excl[lo];
+            const unsigned n = s_excl[lo + 1] - s_excl[lo];
+            const unsigned tile = t0 + lo;
+            unsigned long long src;
+            unsigned rank = idx;
+            if (n <= (unsigned)kSlotsPerTile || idx < (unsigned)kSlotsPerTile) {      // a fixed slot
+                src = (unsigned long long)tile * kSlotsPerTile + idx;
+            } else {                                                                   // ordered tile, overflow area
+                const unsigned long long o = (unsigned long long)s_ovf[lo] + (idx - kSlotsPerTile);
+                if (o >= p.ovf_cap) continue;
+                src = (unsigned long long)p.n_tiles * kSlotsPerTile + o;
+            }
+            const uint4 q = scratch[2 * src];
+            const uint32_t meta = reinterpret_cast<const uint32_t *>(scratch + 2 * src + 1)[0];
+            if (n <= (unsigned)kSlotsPerTile && n > 1u) {
+                rank = 0;
+                const uint4 *first = scratch + 2 * (unsigned long long)tile * kSlotsPerTile;
+                for (unsigned k = 0; k < n; ++k)
+                    rank += (reinterpret_cast<const uint32_t *>(first + 2 * k + 1)[0] & 0xFFFFu) < (meta & 0xFFFFu) ? 1u : 0u;
+            }
+            const unsigned d = s_excl[lo] + rank;
+            if (d < c0 || d >= c1) continue;
+            // first sample of the tile: segments are p.seg_len apart, tiles kWarpTile apart inside one
+            const unsigned seg = tile / p.tiles_per_seg;
+            const unsigned long long off0 = p.base_offset + (unsigned long long)seg * p.seg_len +
+                                            (unsigned long long)(tile - seg * p.tiles_per_seg) * kWarpTile;
+            // scratch slot -> airgpu_frame (three little-endian u64 words): byte-swapped frame words, then
+            // bytes 12, 13 | fixed_bit | reserved, then the absolute sample offset
+            const uint32_t hi32 = __byte_perm(q.w, meta >> 16, 0x7423);
+            unsigned long long *w = s_words + 3 * (d - c0);
+            w[0] = (unsigned long long)__byte_perm(q.x, 0, 0x0123) | ((unsigned long long)__byte_perm(q.y, 0, 0x0123) << 32);
+            w[1] = (unsigned long long)__byte_perm(q.z, 0, 0x0123) | ((unsigned long long)hi32 << 32);
+            w[2] = off0 + (meta & 0xFFFFu);
         }
-        const unsigned idx = r - s_excl[lo];
-        const unsigned n = s_excl[lo + 1] - s_excl[lo];
-        const unsigned tile = t0 + lo;
-        unsigned long long src;
-        unsigned rank = idx;
-        if (n <= (unsigned)kSlotsPerTile) {
-            src = (unsigned long long)tile * kSlotsPerTile + idx;
-        } else if (idx < (unsigned)kSlotsPerTile) {           // ordered tile
-            src = (unsigned long long)tile * kSlotsPerTile + idx;
-        } else {
-            const unsigned long long o = (unsigned long long)s_ovf[lo] + (idx - kSlotsPerTile);
-            if (o >= p.ovf_cap) continue;
-            src = (unsigned long long)p.n_tiles * kSlotsPerTile + o;
-        }
-        const uint4 q = scratch[2 * src];
-        const uint32_t meta = reinterpret_cast<const uint32_t *>(scratch + 2 * src + 1)[0];
-        if (n <= (unsigned)kSlotsPerTile && n > 1u) {
-            rank = 0;
-            const uint4 *first = scratch + 2 * (unsigned long long)tile * kSlotsPerTile;
-            for (unsigned k = 0; k < n; ++k)
-                rank += (reinterpret_cast<const uint32_t *>(first + 2 * k + 1)[0] & 0xFFFFu) < (meta & 0xFFFFu) ? 1u : 0u;
-        }
-        const unsigned long long dst = gbase + s_excl[lo] + rank;
-        if (dst >= p.cap) continue;
-        // first sample of the tile: segments are p.seg_len apart, tiles kWarpTile apart inside one
-        const unsigned seg = tile / p.tiles_per_seg;
-        const unsigned long long off0 = p.base_offset + (unsigned long long)seg * p.seg_len +
-                                        (unsigned long long)(tile - seg * p.tiles_per_seg) * kWarpTile;
-        store_record<kMode>(out, dst, q, meta, off0);
+        __syncthreads();
+        copy_out<kMode>(out, (gbase + c0) * 3ull, s_words, 3u * (c1 - c0));
+        __syncthreads();
     }
 }
 

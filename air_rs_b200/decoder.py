@@ -150,6 +150,9 @@ class AdsbDecoder:
     def graph_begin(self, stream: int) -> None:
         native.check(self._lib.airgpu_graph_begin(self._h, stream))
 
+    def set_capturing(self, on: bool) -> None:
+        native.check(self._lib.airgpu_set_capturing(self._h, 1 if on else 0))
+
     def graph_end(self, stream: int) -> "Graph":
         g = C.c_void_p()
         native.check(self._lib.airgpu_graph_end(self._h, stream, C.byref(g)))

@@ -100,6 +100,7 @@ SYMBOLS = {
     "airgpu_graph_begin": (C.c_int, [_vp, _vp]),
     "airgpu_graph_end": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "airgpu_graph_launch": (C.c_int, [_vp, _vp]),
+    "airgpu_set_capturing": (C.c_int, [_vp, C.c_int]),
     "airgpu_graph_destroy": (None, [_vp]),
     "airgpu_decode_device_peers": (C.c_int, [_vp, _vp, _sz, _sz, _u64, C.POINTER(Peers), _sz, _vp]),
     "airgpu_peer_barrier": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint32, C.c_uint32, _u64, _vp]),

@@ -105,8 +105,11 @@ class ShardedDecoder:
       "auto"   -- multicast if the box offers it, else peers, else nccl; the reason for a downgrade is kept in
                   `exchange_note` and printed to stderr -- never silent.
     multicast / peers: a step is `pieces` x (memset + decode + scan + gather) and ONE barrier kernel
-    (airgpu_peer_barrier: release/acquire flags in the slab), all on the caller's stream, recorded once per parity
-    into a CUDA graph and replayed with one launch per step (`use_graph`).
+    (airgpu_peer_barrier: release/acquire flags in the slab), recorded once per parity into a CUDA graph and replayed
+    with one launch per step (`use_graph`).  Consecutive sub-shards alternate between two library contexts (two
+    workspaces) on two streams forked from the caller's, so the ordering kernels of sub-shard k -- whose stores cross
+    NVLink -- run while the decode kernel of sub-shard k+1 has the SMs; only the LAST sub-shard's exchange is exposed
+    (it is the smallest: see sub_ranges).
 
     Hazards: slabs are double-buffered by step parity and every step ends in a barrier, so a rank can only overwrite
     slot [parity] again two steps later, after every peer has passed the barrier of the step in between -- and
@@ -156,6 +159,10 @@ class ShardedDecoder:
         total_bytes = self.flags_off + 8 * (W + 1)
         if self.exchange in ("multicast", "peers"):
             self.decode_reserved = False
+            # second context + side stream: the exchange of sub-shard k overlaps the decode of sub-shard k+1
+            self._dec_b = type(decoder)(fmt=decoder.fmt, device=decoder.device, ring_slots=1, max_buffer_samples=1024,
+                                        max_frames=64) if P > 1 else None
+            self._side = torch.cuda.Stream(device=self.dev) if P > 1 else None
         else:
             # nccl: local records, all-gathered into `gath` on a high-priority side stream
             self._slab_t = torch.zeros(total_bytes, dtype=torch.uint8, device=self.dev)
@@ -208,9 +215,13 @@ class ShardedDecoder:
         return parity * self.parity_bytes + (k * self.world + r) * self.slot_bytes
 
     # ------------------------------------------------------------------ one step
-    def _enqueue_fused(self, base_ptr: int, parity: int, stream: int) -> None:
-        """pieces x (decode + ordering kernels storing to every rank) + one barrier, on `stream`."""
+    def _enqueue_fused(self, base_ptr: int, parity: int, main) -> None:
+        """pieces x (decode + ordering kernels storing to every rank) alternating between `main` and the side stream
+        (forked from and joined back into `main`), then one barrier on `main`."""
+        if self._side is not None:
+            self._side.wait_stream(main)
         for k, (s, e) in enumerate(self.ranges):
+            dec, stream = (self.dec, main.cuda_stream) if k % 2 == 0 else (self._dec_b, self._side.cuda_stream)
             off = self._slot_off(parity, k, self.rank)
             if self.exchange == "multicast":
                 outs, counts = [self.mc_ptr + off + RECORD_BYTES], [self.mc_ptr + off]
@@ -219,9 +230,11 @@ class ShardedDecoder:
                 order = [(self.rank + q) % self.world for q in range(self.world)]
                 outs = [self.base_ptrs[q] + off + RECORD_BYTES for q in order]
                 counts = [self.base_ptrs[q] + off for q in order]
-            self.dec.decode_device_peers(base_ptr + s * self.bps, e - s + HALO, outs, counts, self.cap, 0, self.first + s,
-                                         stream, multicast=self.exchange == "multicast")
-        self.dec.peer_barrier([p + self.flags_off for p in self.base_ptrs], self.rank, 0, stream)
+            dec.decode_device_peers(base_ptr + s * self.bps, e - s + HALO, outs, counts, self.cap, 0, self.first + s,
+                                    stream, multicast=self.exchange == "multicast")
+        if self._side is not None:
+            main.wait_stream(self._side)
+        self.dec.peer_barrier([p + self.flags_off for p in self.base_ptrs], self.rank, 0, main.cuda_stream)
 
     def step(self, iq, bytes_per_sample: int = None):
         """Queue one pass over this rank's shard (CUDA tensor of interleaved IQ) on the current stream.  Asynchronous."""
@@ -244,7 +257,10 @@ class ShardedDecoder:
         else:
             if not self.decode_reserved:
                 # size the workspace once: nothing may allocate inside a graph capture
-                self.dec.reserve(max(e - s for s, e in self.ranges) + HALO, 0, self.cap)
+                for d in (self.dec, self._dec_b):
+                    if d is not None:
+                        d.reserve(max(e - s for s, e in self.ranges) + HALO, 0, self.cap)
+                        d.set_timing(False)          # sub-shard kernels run on two streams; no per-call events
                 self.decode_reserved = True
             key = (iq.data_ptr(), stream.cuda_stream)
             if self.use_graph and self._graph_key != key:
@@ -255,14 +271,18 @@ class ShardedDecoder:
             if self.use_graph and self._graphs[parity] is None and self.step_no >= 2:
                 # record this parity's sequence once (steps 0 and 1 run eagerly: they warm everything up)
                 self.dec.graph_begin(stream.cuda_stream)
+                if self._dec_b is not None:
+                    self._dec_b.set_capturing(True)      # its calls join the same capture through the side stream
                 try:
-                    self._enqueue_fused(iq.data_ptr(), parity, stream.cuda_stream)
+                    self._enqueue_fused(iq.data_ptr(), parity, stream)
                 finally:
+                    if self._dec_b is not None:
+                        self._dec_b.set_capturing(False)
                     self._graphs[parity] = self.dec.graph_end(stream.cuda_stream)
             if self.use_graph and self._graphs[parity] is not None:
                 self._graphs[parity].launch(stream.cuda_stream)
             else:
-                self._enqueue_fused(iq.data_ptr(), parity, stream.cuda_stream)
+                self._enqueue_fused(iq.data_ptr(), parity, stream)
             with torch.cuda.stream(stream):
                 self.hdr_host[parity].copy_(self._slab[parity, :, :, 0, :8].contiguous().view(-1).view(torch.int64)
                                             .view(len(self.ranges), self.world), non_blocking=True)
@@ -366,3 +386,8 @@ class ShardedDecoder:
             if g is not None:
                 g.close()
         self._graphs = [None, None]
+        if getattr(self, "_dec_b", None) is not None:
+            self._dec_b.close()
+            self._dec_b = None
+        if self.exchange != "nccl":
+            self.dec.set_timing(True)

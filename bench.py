@@ -446,6 +446,7 @@ def run_ours(args):
     if world == 1 and timed_stats["decode_launches"] >= 1:
         kernel_ms, kernel_launches = float(timed_stats["decode_ms"]), int(timed_stats["decode_launches"])
     else:
+        dec.set_timing(True)                    # (the sharded steps switched the per-call events off)
         dec.stats()
         for _ in range(max(3, min(args.steps, 10))):
             decode_resident()

@@ -182,6 +182,9 @@ typedef struct airgpu_graph airgpu_graph;
 int airgpu_graph_begin(airgpu_ctx *ctx, void *stream);
 int airgpu_graph_end(airgpu_ctx *ctx, void *stream, airgpu_graph **out);
 int airgpu_graph_launch(airgpu_graph *graph, void *stream);
+/* A capture may span several streams (forked from the capturing one with events) and several contexts: tell every
+ * OTHER context whose calls land in the capture, so that it neither records timing events nor allocates. */
+int airgpu_set_capturing(airgpu_ctx *ctx, int capturing);
 void airgpu_graph_destroy(airgpu_graph *graph);
 
 /* ---- multi-GPU: the frame exchange fused into the ordering kernels ---------------- *

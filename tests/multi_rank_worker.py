@@ -44,7 +44,7 @@ def main():
     dist.broadcast(ref_n, 0)
     dist.broadcast(ref, 0)
     n_ref = int(ref_n.item())
-    assert n_ref > 100_000
+    assert n_ref > 10_000
     stream = torch.cuda.Stream(device=dev)
     ok_all = True
     for exchange in ("multicast", "peers", "nccl"):
