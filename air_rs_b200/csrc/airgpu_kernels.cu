@@ -1044,7 +1044,9 @@ cudaError_t launch_finalize(const DecodeParams &p, const OutSet &dst, unsigned l
 // then waits until rank q's epoch shows up in its own array (flags[rank][q]).  Every rank runs on its own GPU
 // (never two ranks of one exchange on one device: they would wait for each other's kernel).
 // epoch == 0: the kernel counts for itself in flags[rank][n_ranks] (local memory), so that the same launch can be
-// replayed from a CUDA graph.
+// replayed from a CUDA graph.  Barriers that may run CONCURRENTLY on one GPU (two streams) need separate flag arrays.
+// A peer that does not show up within ~4 s (a crashed rank) is not waited for any longer: the kernel records the
+// failure in flags[rank][n_ranks + 1] and returns, so that nothing spins until a watchdog kills the job.
 __global__ void peer_barrier_kernel(const PeerFlags f)
 {
     __shared__ unsigned long long s_epoch;
@@ -1065,10 +1067,17 @@ __global__ void peer_barrier_kernel(const PeerFlags f)
     unsigned long long *theirs = f.flags[q] + f.rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
     const unsigned long long *mine = f.flags[f.rank] + q;
-    unsigned long long seen;
-    do {
+    unsigned long long seen, t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-    } while (seen < epoch);
+        if (seen >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) {           // nanoseconds
+            f.flags[f.rank][f.n_ranks + 1] = epoch;      // sticky: "the barrier of this epoch timed out"
+            break;
+        }
+    }
 }
 
 cudaError_t launch_peer_barrier(const PeerFlags &f, cudaStream_t stream)

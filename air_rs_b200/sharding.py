@@ -106,15 +106,17 @@ class ShardedDecoder:
                   `exchange_note` and printed to stderr -- never silent.
     multicast / peers: a step is `pieces` x (memset + decode + scan + gather) and ONE barrier kernel
     (airgpu_peer_barrier: release/acquire flags in the slab), recorded once per parity into a CUDA graph and replayed
-    with one launch per step (`use_graph`).  Consecutive sub-shards alternate between two library contexts (two
-    workspaces) on two streams forked from the caller's, so the ordering kernels of sub-shard k -- whose stores cross
-    NVLink -- run while the decode kernel of sub-shard k+1 has the SMs; only the LAST sub-shard's exchange is exposed
-    (it is the smallest: see sub_ranges).
+    with one launch per step (`use_graph`).  TWO STEPS ARE IN FLIGHT: even and odd steps run on two streams (forked
+    from the caller's) with two library contexts (two workspaces) and the two slab parities, so the ordering kernels,
+    the NVLink traffic and the barrier of step t -- an all-gather lands (W-1)/W of the whole list in every GPU,
+    ~0.15 ms of link time per step at 8 GPUs -- run while the decode kernel of step t+1 has the SMs, and the first
+    CTAs of step t+1 fill the tail of step t's decode kernel.  `wait()` joins both streams into the caller's.
 
-    Hazards: slabs are double-buffered by step parity and every step ends in a barrier, so a rank can only overwrite
-    slot [parity] again two steps later, after every peer has passed the barrier of the step in between -- and
-    therefore has executed everything it queued on its stream before that step, including the reads of `finish()`.
-    Consumers of `finish(concat=False)` views must queue their reads (on the same stream) before calling `step()` twice.
+    Hazards: slabs are double-buffered by step parity and every step ends in a barrier.  Step t+2 runs on the same
+    stream as step t, i.e. after step t's barrier: by then every peer has finished writing step t's slab AND has
+    passed its own barrier of step t, hence has executed everything it queued before its step t+2 on that stream --
+    including the reads `finish()` queued there.  Consumers of `finish(concat=False)` views must queue their reads
+    before calling `step()` twice.
 
     Result order: rank-major, piece-minor == ascending offset == the reference's order.
     """
@@ -146,7 +148,8 @@ class ShardedDecoder:
         self.rows = cap + 1
         self.slot_bytes = self.rows * RECORD_BYTES
         self.parity_bytes = P * W * self.slot_bytes
-        self.flags_off = 2 * self.parity_bytes                    # [W + 1] u64: epochs seen from each rank, own counter
+        self.flags_off = 2 * self.parity_bytes                    # per lane [W + 2] u64: epochs seen from each rank, own counter, time-out mark
+        self.flags_bytes = 8 * (W + 2)
         self.hdr_host = torch.zeros((2, P, W), dtype=torch.int64).pin_memory()
         self.step_no = 0
         self.use_graph = use_graph
@@ -156,13 +159,13 @@ class ShardedDecoder:
         self.exchange_note = ""
         self.symm = None
         self.exchange = self._pick_exchange(exchange)
-        total_bytes = self.flags_off + 8 * (W + 1)
+        total_bytes = self.flags_off + 2 * self.flags_bytes
         if self.exchange in ("multicast", "peers"):
             self.decode_reserved = False
-            # second context + side stream: the exchange of sub-shard k overlaps the decode of sub-shard k+1
-            self._dec_b = type(decoder)(fmt=decoder.fmt, device=decoder.device, ring_slots=1, max_buffer_samples=1024,
-                                        max_frames=64) if P > 1 else None
-            self._side = torch.cuda.Stream(device=self.dev) if P > 1 else None
+            # two lanes (even / odd steps): a context and a stream each
+            self._decs = [decoder, type(decoder)(fmt=decoder.fmt, device=decoder.device, ring_slots=1,
+                                                 max_buffer_samples=1024, max_frames=64)]
+            self._lanes = [torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)]
         else:
             # nccl: local records, all-gathered into `gath` on a high-priority side stream
             self._slab_t = torch.zeros(total_bytes, dtype=torch.uint8, device=self.dev)
@@ -183,7 +186,7 @@ class ShardedDecoder:
             raise ValueError(f"unknown exchange back end {want!r}")
         if want == "nccl" or self.world == 1 and want == "auto":
             return "nccl"
-        total_bytes = self.flags_off + 8 * (self.world + 1)
+        total_bytes = self.flags_off + 2 * self.flags_bytes
         try:
             import torch.distributed._symmetric_memory as symm
 
@@ -215,13 +218,10 @@ class ShardedDecoder:
         return parity * self.parity_bytes + (k * self.world + r) * self.slot_bytes
 
     # ------------------------------------------------------------------ one step
-    def _enqueue_fused(self, base_ptr: int, parity: int, main) -> None:
-        """pieces x (decode + ordering kernels storing to every rank) alternating between `main` and the side stream
-        (forked from and joined back into `main`), then one barrier on `main`."""
-        if self._side is not None:
-            self._side.wait_stream(main)
+    def _enqueue_fused(self, base_ptr: int, parity: int, stream: int) -> None:
+        """pieces x (decode + ordering kernels storing to every rank) + one barrier, on the lane's stream."""
+        dec = self._decs[parity]
         for k, (s, e) in enumerate(self.ranges):
-            dec, stream = (self.dec, main.cuda_stream) if k % 2 == 0 else (self._dec_b, self._side.cuda_stream)
             off = self._slot_off(parity, k, self.rank)
             if self.exchange == "multicast":
                 outs, counts = [self.mc_ptr + off + RECORD_BYTES], [self.mc_ptr + off]
@@ -232,62 +232,60 @@ class ShardedDecoder:
                 counts = [self.base_ptrs[q] + off for q in order]
             dec.decode_device_peers(base_ptr + s * self.bps, e - s + HALO, outs, counts, self.cap, 0, self.first + s,
                                     stream, multicast=self.exchange == "multicast")
-        if self._side is not None:
-            main.wait_stream(self._side)
-        self.dec.peer_barrier([p + self.flags_off for p in self.base_ptrs], self.rank, 0, main.cuda_stream)
+        # each lane has its own flag arrays: the barriers of two consecutive steps may run at the same time
+        dec.peer_barrier([p + self.flags_off + parity * self.flags_bytes for p in self.base_ptrs], self.rank, 0, stream)
 
     def step(self, iq, bytes_per_sample: int = None):
-        """Queue one pass over this rank's shard (CUDA tensor of interleaved IQ) on the current stream.  Asynchronous."""
+        """Queue one pass over this rank's shard (CUDA tensor of interleaved IQ).  Asynchronous; ordered after the
+        work already queued on the current stream.  Call wait() (or finish()) before the current stream uses the result."""
         import torch
 
         if bytes_per_sample is not None:
             self.bps = bytes_per_sample
         cur = torch.cuda.current_stream(self.dev)
-        stream = cur
-        if cur.cuda_stream == 0:
-            # the legacy default stream: the library would fall back to its own (non-blocking) compute stream, which is
-            # not ordered against it -- run the step on a private stream bracketed by the default stream instead
-            if self._own_stream is None:
-                self._own_stream = torch.cuda.Stream(device=self.dev)
-            stream = self._own_stream
-            stream.wait_stream(cur)
         parity = self.step_no & 1
         if self.exchange == "nccl":
+            stream = cur
+            if cur.cuda_stream == 0:
+                # the legacy default stream: the library would fall back to its own (non-blocking) compute stream, which
+                # is not ordered against it -- run the step on a private stream bracketed by the default stream instead
+                if self._own_stream is None:
+                    self._own_stream = torch.cuda.Stream(device=self.dev)
+                stream = self._own_stream
+                stream.wait_stream(cur)
             self._step_nccl(iq, parity, stream)
+            if stream is not cur:
+                cur.wait_stream(stream)
         else:
+            stream = self._lanes[parity]
+            stream.wait_stream(cur)                  # the producer of `iq`
             if not self.decode_reserved:
-                # size the workspace once: nothing may allocate inside a graph capture
-                for d in (self.dec, self._dec_b):
-                    if d is not None:
-                        d.reserve(max(e - s for s, e in self.ranges) + HALO, 0, self.cap)
-                        d.set_timing(False)          # sub-shard kernels run on two streams; no per-call events
+                # size the workspaces once: nothing may allocate inside a graph capture
+                for d in self._decs:
+                    d.reserve(max(e - s for s, e in self.ranges) + HALO, 0, self.cap)
+                    d.set_timing(False)
                 self.decode_reserved = True
-            key = (iq.data_ptr(), stream.cuda_stream)
+            key = iq.data_ptr()
             if self.use_graph and self._graph_key != key:
                 for g in self._graphs:
                     if g is not None:
                         g.close()
                 self._graphs, self._graph_key = [None, None], key
+            dec = self._decs[parity]
             if self.use_graph and self._graphs[parity] is None and self.step_no >= 2:
-                # record this parity's sequence once (steps 0 and 1 run eagerly: they warm everything up)
-                self.dec.graph_begin(stream.cuda_stream)
-                if self._dec_b is not None:
-                    self._dec_b.set_capturing(True)      # its calls join the same capture through the side stream
+                # record this lane's sequence once (steps 0 and 1 run eagerly: they warm everything up)
+                dec.graph_begin(stream.cuda_stream)
                 try:
-                    self._enqueue_fused(iq.data_ptr(), parity, stream)
+                    self._enqueue_fused(iq.data_ptr(), parity, stream.cuda_stream)
                 finally:
-                    if self._dec_b is not None:
-                        self._dec_b.set_capturing(False)
-                    self._graphs[parity] = self.dec.graph_end(stream.cuda_stream)
+                    self._graphs[parity] = dec.graph_end(stream.cuda_stream)
             if self.use_graph and self._graphs[parity] is not None:
                 self._graphs[parity].launch(stream.cuda_stream)
             else:
-                self._enqueue_fused(iq.data_ptr(), parity, stream)
+                self._enqueue_fused(iq.data_ptr(), parity, stream.cuda_stream)
             with torch.cuda.stream(stream):
                 self.hdr_host[parity].copy_(self._slab[parity, :, :, 0, :8].contiguous().view(-1).view(torch.int64)
                                             .view(len(self.ranges), self.world), non_blocking=True)
-        if stream is not cur:
-            cur.wait_stream(stream)
         self.last_stream = stream
         self.step_no += 1
 
@@ -323,8 +321,12 @@ class ShardedDecoder:
         """Make the current stream wait for the exchange of the last queued step (a timed region ends here)."""
         import torch
 
+        cur = torch.cuda.current_stream(self.dev)
         if self.exchange == "nccl":
-            torch.cuda.current_stream(self.dev).wait_stream(self.comm)
+            cur.wait_stream(self.comm)
+        else:
+            for st in self._lanes:
+                cur.wait_stream(st)
 
     def finish(self, concat: bool = True):
         """Wait for the last queued step; returns (frames [n, 24] in global order, n)."""
@@ -334,8 +336,15 @@ class ShardedDecoder:
             raise RuntimeError("finish() before any step()")
         if self.exchange == "nccl":
             self.comm.synchronize()
+        else:
+            for st in self._lanes:
+                st.synchronize()
         self.last_stream.synchronize()
         parity = (self.step_no - 1) & 1
+        if self.exchange != "nccl":
+            marks = self._slab_t[self.flags_off: self.flags_off + 2 * self.flags_bytes].view(torch.int64).view(2, self.world + 2)
+            if int(marks[:, self.world + 1].max().item()) != 0:
+                raise RuntimeError("a frame-exchange barrier timed out (a peer rank did not arrive within 4 s)")
         counts = self.hdr_host[parity].clone()
         m = int(counts.max())
         if m > self.cap:
@@ -386,8 +395,8 @@ class ShardedDecoder:
             if g is not None:
                 g.close()
         self._graphs = [None, None]
-        if getattr(self, "_dec_b", None) is not None:
-            self._dec_b.close()
-            self._dec_b = None
         if self.exchange != "nccl":
+            for d in self._decs[1:]:
+                d.close()
+            self._decs = self._decs[:1]
             self.dec.set_timing(True)

@@ -336,7 +336,7 @@ def run_ours(args):
     stream = tstream.cuda_stream
     assert stream != 0
     state = {"frames": 0, "gathered": None}
-    pieces = 1 if world == 1 else int(os.environ.get("AIRGPU_PIECES", 2))
+    pieces = int(os.environ.get("AIRGPU_PIECES", 1))
     sharded = (sharding.ShardedDecoder(dec, n_local, a, pieces=pieces, exchange=os.environ.get("AIRGPU_EXCHANGE", "auto"),
                                        use_graph=os.environ.get("AIRGPU_GRAPH", "1") != "0")
                if world > 1 else None)

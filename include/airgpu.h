@@ -211,8 +211,11 @@ int airgpu_decode_device_peers(airgpu_ctx *ctx, const void *d_iq, size_t n_sampl
  * n_ranks epochs (zero-initialised) as mapped in this process; every rank calls it with
  * the same, increasing `epoch` (>= 1).  After it, the records every rank stored before its
  * own call are visible here.  epoch = 0: the kernel keeps the count itself in
- * flags[rank][n_ranks] (the arrays then hold n_ranks + 1 words), so that one recorded
- * launch can be replayed from a CUDA graph.  One rank per GPU: two ranks of one
+ * flags[rank][n_ranks], so that one recorded launch can be replayed from a CUDA graph.
+ * The arrays hold n_ranks + 2 words: a peer that does not arrive within ~4 s (a crashed
+ * rank) is given up on and the epoch is recorded in flags[rank][n_ranks + 1] (non-zero =
+ * a barrier timed out; the caller checks it).  Barriers that may run concurrently on one
+ * GPU (two streams) need separate flag arrays.  One rank per GPU: two ranks of one
  * exchange on the same device would wait for each other's kernel. */
 int airgpu_peer_barrier(airgpu_ctx *ctx, uint64_t *const *flags, uint32_t n_ranks, uint32_t rank,
                         uint64_t epoch, void *stream);
