@@ -102,7 +102,8 @@ class ShardedDecoder:
       "peers"  -- same slab, the gather kernel stores each record to every rank's peer-mapped address ((W-1)x egress).
       "nccl"   -- records stay local, one ncclAllGather per sub-shard on a side stream (the portable fallback, and what
                   the CPU tests run over gloo).
-      "auto"   -- multicast if the box offers it, else peers, else nccl; the reason for a downgrade is kept in
+      "auto"   -- peers (measured faster than multicast once two steps are in flight: its stores hide behind the next
+                  decode), else nccl when the box has no symmetric memory; the reason for a downgrade is kept in
                   `exchange_note` and printed to stderr -- never silent.
     multicast / peers: a step is `pieces` x (memset + decode + scan + gather) and ONE barrier kernel
     (airgpu_peer_barrier: release/acquire flags in the slab), recorded once per parity into a CUDA graph and replayed
@@ -121,7 +122,7 @@ class ShardedDecoder:
     Result order: rank-major, piece-minor == ascending offset == the reference's order.
     """
 
-    def __init__(self, decoder, n_local: int, first_sample: int, pieces: int = 2, cap_per_piece: int = 0,
+    def __init__(self, decoder, n_local: int, first_sample: int, pieces: int = 0, cap_per_piece: int = 0,
                  group=None, exchange: str = "auto", use_graph: bool = True, bytes_per_sample: int = 2):
         import torch
         import torch.distributed as dist
@@ -136,8 +137,17 @@ class ShardedDecoder:
         weights = None
         if os.environ.get("AIRGPU_PIECE_WEIGHTS"):
             weights = [float(x) for x in os.environ["AIRGPU_PIECE_WEIGHTS"].split(",")]
-        self.ranges = sub_ranges(cands, pieces, weights)          # same number of exchanges on every rank
         self.first = first_sample
+        self.exchange_note = ""
+        self.symm = None
+        self._slab_t = None
+        # the slab must be sized before the back end is probed (the symmetric allocation is the probe), so the
+        # number of sub-shards is fixed first: 0 = automatic -- one for the fused back ends (two steps in flight hide
+        # the exchange), two for the NCCL fallback (its all-gather of sub-shard 0 overlaps the decode of sub-shard 1)
+        want_nccl = exchange == "nccl" or (self.world == 1 and exchange == "auto")
+        if pieces <= 0:
+            pieces = 2 if want_nccl else 1
+        self.ranges = sub_ranges(cands, pieces, weights)          # same number of exchanges on every rank
         cap = cap_per_piece or max(1 << 14, (max(e - s for s, e in self.ranges) + HALO) // 200)   # ~4x dense traffic
         if self.world > 1:   # every rank must use the same row count
             c = torch.tensor([cap], dtype=torch.int64, device=self.dev)
@@ -156,8 +166,6 @@ class ShardedDecoder:
         self._graphs = [None, None]
         self._graph_key = None
         self._own_stream = None
-        self.exchange_note = ""
-        self.symm = None
         self.exchange = self._pick_exchange(exchange)
         total_bytes = self.flags_off + 2 * self.flags_bytes
         if self.exchange in ("multicast", "peers"):
@@ -207,11 +215,12 @@ class ShardedDecoder:
             return "nccl"
         if want == "multicast" and not self.mc_ptr:
             raise RuntimeError("no NVSwitch multicast mapping for the symmetric slab on this box")
-        if want in ("auto", "multicast") and self.mc_ptr:
+        if want == "multicast" and self.mc_ptr:
             return "multicast"
-        if want == "auto":
-            self.exchange_note = "no multicast mapping; plain stores to every peer"
-            print(f"[airgpu sharding] {self.exchange_note}", file=sys.stderr)
+        # "auto" takes plain peer stores even when the box offers a multicast mapping.  Measured on this pool
+        # (profiles/r2_exchange_*.txt): with two steps in flight the plain stores to the peers' mapped slabs hide
+        # completely behind the next step's decode kernel (2 GPUs: 2.161 ms per step vs 2.164 ms for the decode
+        # alone), while multimem.st stores do not (2.245 ms at 2 GPUs, 0.710 ms vs 0.523 ms of decode at 8 GPUs).
         return "peers"
 
     def _slot_off(self, parity: int, k: int, r: int) -> int:

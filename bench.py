@@ -336,7 +336,7 @@ def run_ours(args):
     stream = tstream.cuda_stream
     assert stream != 0
     state = {"frames": 0, "gathered": None}
-    pieces = int(os.environ.get("AIRGPU_PIECES", 1))
+    pieces = int(os.environ.get("AIRGPU_PIECES", 0))       # 0: automatic (sharding.ShardedDecoder)
     sharded = (sharding.ShardedDecoder(dec, n_local, a, pieces=pieces, exchange=os.environ.get("AIRGPU_EXCHANGE", "auto"),
                                        use_graph=os.environ.get("AIRGPU_GRAPH", "1") != "0")
                if world > 1 else None)
@@ -579,11 +579,14 @@ def run_ours(args):
             "config": workload_config(world, total),
             "frames_per_step": state["frames"],
             "gpu_launches": launches * args.steps,
-            "pieces_per_rank": pieces,
+            "pieces_per_rank": (len(sharded.ranges) if sharded is not None else 1),
+            "steps_in_flight": (2 if sharded is not None and sharded.exchange != "nccl" else 1),
             "frame_exchange": (sharded.exchange if sharded is not None else None),
             "frame_exchange_detail": (None if sharded is None else {
-                "multicast": "ordering kernels store each record once to an NVSwitch multicast address (multimem.st)",
-                "peers": "ordering kernels store each record to every rank's peer-mapped slab",
+                "multicast": "ordering kernels store each record once to an NVSwitch multicast address (multimem.st); the "
+                             "exchange and barrier of step t overlap the decode of step t+1 (two lanes)",
+                "peers": "ordering kernels store each record to every rank's peer-mapped slab (16-byte coalesced stores "
+                         "over NVLink); the exchange and barrier of step t overlap the decode of step t+1 (two lanes)",
                 "nccl": "ncclAllGather per sub-shard on a side stream"}[sharded.exchange]),
             "frame_exchange_note": (sharded.exchange_note if sharded is not None else None),
             "cuda_graph": (bool(sharded.use_graph and sharded.exchange != "nccl") if sharded is not None else False),
