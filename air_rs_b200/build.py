@@ -1,9 +1,11 @@
 """In-tree nvcc build of libairgpu.so (sm_100a only)."""
 from __future__ import annotations
 
+import fcntl
 import os
 import shutil
 import subprocess
+from contextlib import contextmanager
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -30,24 +32,51 @@ def is_stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "airgpu.h"]
+    deps = ([CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) +
+            [PKG.parent / "include" / "airgpu.h", PKG.parent / "include" / "airgpu_synth.h"])
     return any(d.exists() and d.stat().st_mtime > t for d in deps)
+
+
+@contextmanager
+def _build_lock():
+    """One builder at a time: every rank of a torchrun job imports the package (and may find the library stale) at
+    the same moment.  The others wait here and then find it fresh."""
+    LIBDIR.mkdir(exist_ok=True)
+    with open(LIBDIR / ".build.lock", "w") as fh:
+        fcntl.flock(fh, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(fh, fcntl.LOCK_UN)
+
+
+def _compile(cmd, out: Path) -> subprocess.CompletedProcess:
+    """Run a compiler that writes to a temporary file next to `out`, then move it into place atomically: a process
+    that is loading the library never sees a half-written file."""
+    tmp = out.with_name(f".{out.name}.{os.getpid()}.tmp")
+    full = [c if c != "@OUT@" else str(tmp) for c in cmd]
+    r = subprocess.run(full, capture_output=True, text=True)
+    if r.returncode != 0:
+        tmp.unlink(missing_ok=True)
+        raise RuntimeError(f"{full[0]} failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, out)
+    return r
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source into air_rs_b200/_lib/libairgpu.so."""
     if (not force and not is_stale()) or "AIRGPU_LIB" in os.environ:
         return LIB
-    LIBDIR.mkdir(exist_ok=True)
-    srcs = [str(CSRC / s) for s in SOURCES]
-    cmd = [nvcc(), *NVCC_FLAGS, "-o", str(LIB), *srcs]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    with _build_lock():
+        if not force and not is_stale():           # another process built it while this one waited
+            return LIB
+        srcs = [str(CSRC / s) for s in SOURCES]
+        cmd = [nvcc(), *NVCC_FLAGS, "-o", "@OUT@", *srcs]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = _compile(cmd, LIB)
+        if verbose:
+            print(r.stderr)
     return LIB
 
 
@@ -62,11 +91,9 @@ def build_host(force: bool = False) -> Path:
     stale = (not HOST_BIN.exists()) or HOST_BIN.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime,
                                                                       LIB.stat().st_mtime)
     if force or stale:
-        cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-Wall", str(src), "-o", str(HOST_BIN),
-               f"-L{LIBDIR}", "-lairgpu", "-Wl,-rpath,$ORIGIN"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+        with _build_lock():
+            _compile(["g++", "-O2", "-std=c++17", "-pthread", "-Wall", str(src), "-o", "@OUT@",
+                      f"-L{LIBDIR}", "-lairgpu", "-Wl,-rpath,$ORIGIN"], HOST_BIN)
     return HOST_BIN
 
 
@@ -79,10 +106,8 @@ def build_host_lib(force: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     stale = (not HOST_LIB.exists()) or HOST_LIB.stat().st_mtime < max(f.stat().st_mtime for f in srcs)
     if force or stale:
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", str(HOST_LIB), str(srcs[0])]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+        with _build_lock():
+            _compile(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", "@OUT@", str(srcs[0])], HOST_LIB)
     return HOST_LIB
 
 
