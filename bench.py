@@ -366,6 +366,7 @@ def run_ours(args):
     sharded = (sharding.ShardedDecoder(dec, n_local, a, pieces=pieces, exchange=os.environ.get("AIRGPU_EXCHANGE", "auto"),
                                        use_graph=os.environ.get("AIRGPU_GRAPH", "1") != "0")
                if world > 1 else None)
+    fallback_note = None
 
     def decode_resident():
         dec.decode_device(iq.data_ptr(), n_local, out.data_ptr(), cap, 0, a, d_count.data_ptr(), stream)
@@ -418,7 +419,30 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     dec.stats()                                 # forget the decode-kernel events of everything before the timed region
-    ms_total = timed(step, args.steps, max(args.warmup, 4 if world > 1 else 3), sampler)   # N > 1: both graph parities recorded in warm-up
+    n_warm = max(args.warmup, 4 if world > 1 else 3)        # N > 1: both graph lanes are recorded during warm-up
+    if world == 1:
+        ms_total = timed(step, args.steps, n_warm, sampler)
+    else:
+        # A rank whose exchange barrier timed out (a peer did not arrive: sharding.finish() raises) must not leave
+        # the others waiting in a collective: every rank reports, all decide together, and the run is repeated with
+        # the NCCL all-gather back end -- slower, stated in the line -- instead of dying without a number.
+        err = 0
+        try:
+            if os.environ.get("AIRGPU_FORCE_EXCHANGE_ERROR") == "1":
+                raise RuntimeError("forced (AIRGPU_FORCE_EXCHANGE_ERROR=1)")
+            ms_total = timed(step, args.steps, n_warm, sampler)
+        except (RuntimeError, ValueError) as e:
+            err, fallback_note = 1, f"{type(e).__name__}: {e}"
+        flag = torch.tensor([err], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            fallback_note = (f"fused frame exchange ({sharded.exchange}) failed on "
+                             f"{'this' if err else 'another'} rank ({fallback_note}); repeated with the NCCL all-gather")
+            print(f"[bench] {fallback_note}", file=sys.stderr)
+            torch.cuda.synchronize()
+            sharded = sharding.ShardedDecoder(dec, n_local, a, pieces=2, exchange="nccl")
+            sampler.samples.clear()
+            ms_total = timed(step, args.steps, n_warm, sampler)
     timed_stats = dec.stats()                   # N = 1: the decode kernel's own events INSIDE the timed region
     sampler.stop()
     ms_step = ms_total / args.steps
@@ -627,7 +651,7 @@ def run_ours(args):
                 "peers": "ordering kernels store each record to every rank's peer-mapped slab (16-byte coalesced stores "
                          "over NVLink); the exchange and barrier of step t overlap the decode of step t+1 (two lanes)",
                 "nccl": "ncclAllGather per sub-shard on a side stream"}[sharded.exchange]),
-            "frame_exchange_note": (sharded.exchange_note if sharded is not None else None),
+            "frame_exchange_note": ((fallback_note or sharded.exchange_note) if sharded is not None else None),
             "cuda_graph": (bool(sharded.use_graph and sharded.exchange != "nccl") if sharded is not None else False),
             "gathered_list_checks_out": exchange_ok,
             "gathered_equals_single_gpu_decode_on_rank0": truth_ok,
