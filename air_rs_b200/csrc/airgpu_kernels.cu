@@ -73,6 +73,10 @@ constexpr SynTable make_syn()
     }
     return t;
 }
+// compile-time known answers (T[0] = 0x3935EA ... T[87] = 0xFFF409; a parity bit is its own syndrome)
+static_assert(make_syn().v[0] == 0x3935EAu && make_syn().v[87] == 0xFFF409u, "CRC-24 single-bit syndromes (crc.rs:10-40)");
+static_assert(make_syn().v[88] == 0x800000u && make_syn().v[111] == 0x000001u, "parity-bit syndromes");
+
 // The slicer gives lane l the frame bits 31 - l + 32 r (r = 0..3), so a lane needs exactly four
 // syndromes: one 16-byte load.  Entry .w is zero for the lanes that have no bit in round 3.
 struct SynLanes {
@@ -90,6 +94,8 @@ constexpr SynLanes make_syn_lanes()
     }
     return s;
 }
+static_assert(make_syn_lanes().v[31].x == 0x3935EAu && make_syn_lanes().v[8].z == 0xFFF409u && make_syn_lanes().v[15].w == 0u &&
+              make_syn_lanes().v[16].w == 0x000001u, "lane layout of the syndromes: frame bit 32 r + 31 - lane");
 __device__ const SynLanes g_syn_lanes = make_syn_lanes();
 
 // ---- per-sample level -------------------------------------------------------
