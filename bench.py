@@ -561,7 +561,7 @@ def run_ours(args):
         # airgpu_decode is synchronous (it returns the frames), so CUDA events bracket host-side work too
         e2e_ms_step = e2e_ms / k2
         h2d_ms = float(np.median(got["h2d_ms"][1:] or got["h2d_ms"]))
-        per_rank = torch.tensor([h2d_ms, 2.0 * n_local / (h2d_ms * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        per_rank = torch.tensor([h2d_ms, (2.0 * n_local / (h2d_ms * 1e-3) / 1e9) if h2d_ms > 0 else 0.0], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(per_rank) for _ in range(world)] if world > 1 else [per_rank]
         if world > 1:
             dist.all_gather(allr, per_rank)
