@@ -80,3 +80,16 @@ def test_product_never_imports_the_oracle():
         text = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
         assert "adsb_oracle" not in text and "oracle_c" not in text and "oracle_np" not in text, f
+
+
+def test_c_consumer_links_and_runs(tmp_path):
+    """A C99 program compiled against include/airgpu.h and linked with libairgpu.so runs: on a box without a GPU it
+    sees AIRGPU_ERR_NO_DEVICE (there is no CPU fallback), on a B200 it decodes through the ABI."""
+    lib = build.build()
+    exe = tmp_path / "c_consumer"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}",
+                    str(ROOT / "tests" / "c_consumer.c"), "-o", str(exe), f"-L{lib.parent}", "-lairgpu",
+                    f"-Wl,-rpath,{lib.parent}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi 2" in r.stdout
